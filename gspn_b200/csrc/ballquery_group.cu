@@ -1,0 +1,347 @@
+// ballquery_group.cu -- query_ball_point (tf_grouping_g.cu:6-39) and the fused
+// ball-query + group_point of sample_and_group (utils/pointnet_util.py:40-48).
+//
+// Reference: one CTA per cloud, one thread per query, each thread streams all n points from
+// global memory with a divergent early exit; then a second kernel copies rows one scalar at a
+// time.  Here:
+//   * a warp owns QPW queries; the cloud streams through shared memory in tiles that are fetched
+//     by the TMA bulk-copy engine (cp.async.bulk + mbarrier, double buffered) when the cloud is
+//     16-byte aligned, by coalesced loads otherwise;
+//   * each lane tests one point per step against the warp's queries; hits are compacted IN INDEX
+//     ORDER with __ballot_sync + popc prefix, so "first nsample in index order" and the first-hit
+//     back-fill of the reference hold exactly;
+//   * the predicate max(sqrtf(s),1e-20f) < radius is evaluated as  !(s > s_max)  with s_max the
+//     largest float whose correctly-rounded square root is below radius (computed on the host by
+//     bisection over float bit patterns) -- identical decisions, no sqrt in the inner loop;
+//   * the same warp then writes its queries' neighbourhood rows [features | xyz - centre | 0]
+//     either as plain f32 rows or straight into the bf16 128B-swizzled tile image that
+//     tcgen05.mma consumes (common.cuh), so the grouped tensor is written once, coalesced,
+//     in the layout its only consumer wants.
+#include <cmath>
+#include <cstring>
+#include "common.cuh"
+
+namespace gspn {
+
+constexpr int kBQWarps = 8;
+constexpr int kBQThreads = kBQWarps * 32;
+constexpr int kBQTile = 2048;  // points per smem tile (24 KiB as packed xyz)
+
+// largest float s with max(sqrtf(s),1e-20f) < radius, or -1 if no s >= 0 qualifies.
+static float ball_threshold(float radius) {
+    if (!(radius > 1e-20f)) return -1.0f;
+    if (std::isinf(radius)) return 3.402823466e38f;
+    uint32_t lo = 0, hi = 0x7F7FFFFFu;  // invariant: sqrtf(lo) < radius (sqrtf(0)=0 < radius)
+    auto ok = [&](uint32_t bits) { float s; std::memcpy(&s, &bits, 4); return sqrtf(s) < radius; };
+    if (ok(hi)) return 3.402823466e38f;
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (ok(mid)) lo = mid; else hi = mid;
+    }
+    float s; std::memcpy(&s, &lo, 4);
+    return s;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (UBLKCP); bytes multiple of 16, both addresses 16B aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct GroupArgs {
+    const float *shift;  // optional (b,m,3) extra shift (multi_encoding_net, model_rpointnet.py:56-57)
+    const void *points;          // (b,n,c) f32 or bf16, may be null
+    int c;
+    int points_bf16;
+    void *grouped;  // null -> indices only
+    int grouped_bf16;
+    int ld;
+};
+
+// one element of a neighbourhood row: [ features(c) | (xyz - centre) - shift | 0 ]
+struct RowSrc {
+    const float *pts_f;
+    const __nv_bfloat16 *pts_h;
+    const float *xyz;  // cloud base
+    int c;
+    float qx, qy, qz, sx, sy, sz;
+    bool has_shift;
+    __device__ __forceinline__ float at(int ii, int col) const {
+        if (col < c) {
+            size_t o = (size_t)ii * c + col;
+            return pts_h ? __bfloat162float(pts_h[o]) : __ldg(pts_f + o);
+        }
+        if (col < c + 3) {
+            int a = col - c;
+            float q = a == 0 ? qx : (a == 1 ? qy : qz);
+            float v = __fsub_rn(__ldg(xyz + (size_t)ii * 3 + a), q);  // grouped_xyz -= new_xyz (pointnet_util.py:42)
+            if (has_shift) v = __fsub_rn(v, a == 0 ? sx : (a == 1 ? sy : sz));  // -= shift_pred (model_rpointnet.py:56-57)
+            return v;
+        }
+        return 0.f;
+    }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// write one neighbourhood (nsample rows) of query (cloud,j); sidx = the row's indices in smem
+__device__ __forceinline__ void write_group(const GroupArgs &g, int n, int m, int nsample, int cloud, int j, const int *sidx,
+                                            const float *__restrict__ xyz, float qx, float qy, float qz, int lane) {
+    const long row0 = ((long)cloud * m + j) * nsample;
+    RowSrc src;
+    src.c = g.c;
+    src.pts_f = g.points_bf16 ? nullptr : (const float *)g.points + (size_t)cloud * n * g.c;
+    src.pts_h = g.points_bf16 ? (const __nv_bfloat16 *)g.points + (size_t)cloud * n * g.c : nullptr;
+    src.xyz = xyz + (size_t)cloud * n * 3;
+    src.qx = qx; src.qy = qy; src.qz = qz;
+    src.has_shift = g.shift != nullptr;
+    src.sx = src.sy = src.sz = 0.f;
+    if (src.has_shift) {
+        const float *sp = g.shift + ((size_t)cloud * m + j) * 3;
+        src.sx = __ldg(sp); src.sy = __ldg(sp + 1); src.sz = __ldg(sp + 2);
+    }
+    if (!g.grouped_bf16) {
+        // lanes sweep the (row, column) space of the block; columns are contiguous in memory
+        float *out = (float *)g.grouped;
+        const int ld = g.ld;
+        for (int e = lane; e < nsample * ld; e += 32) {
+            int s = e / ld, col = e - s * ld;
+            out[(row0 + s) * ld + col] = src.at(sidx[s], col);
+        }
+        return;
+    }
+    // bf16 tile image: one 16-byte chunk (8 columns) per lane-step
+    unsigned char *img = (unsigned char *)g.grouped;
+    const int chunks = g.ld >> 3;
+    const bool vec_f = src.pts_f && (g.c % 4 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_f) & 15u) == 0);
+    const bool vec_h = src.pts_h && (g.c % 8 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_h) & 15u) == 0);
+    for (int e = lane; e < nsample * chunks; e += 32) {
+        int s = e / chunks, ch = e - s * chunks;
+        int ii = sidx[s];
+        uint4 pk;
+        if (ch * 8 + 8 <= g.c && vec_h) {
+            pk = __ldg(reinterpret_cast<const uint4 *>(src.pts_h + (size_t)ii * g.c + ch * 8));
+        } else if (ch * 8 + 8 <= g.c && vec_f) {
+            const float4 *fp = reinterpret_cast<const float4 *>(src.pts_f + (size_t)ii * g.c + ch * 8);
+            float4 a = __ldg(fp), b = __ldg(fp + 1);
+            pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+        } else {
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[t] = src.at(ii, ch * 8 + t);
+            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+        }
+        *reinterpret_cast<uint4 *>(img + tile_chunk_offset(row0 + s, ch, g.ld)) = pk;
+    }
+}
+
+// grid = (ceil(m / (kBQWarps*QPW)), b).  dynamic smem: 2 point tiles + per-warp index rows.
+template <int QPW>
+__global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, float s_max, int nsample, const float *__restrict__ xyz1,
+                                                               const float *__restrict__ xyz2, int *__restrict__ idx,
+                                                               int *__restrict__ pts_cnt, GroupArgs g) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);                        // [2][kBQTile*3]
+    int *widx = reinterpret_cast<int *>(smem_raw + 2 * kBQTile * 3 * 4);       // [kBQWarps][QPW][nsample]
+    __shared__ __align__(8) uint64_t full[2];
+
+    const int cloud = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *p = xyz1 + (size_t)cloud * n * 3;
+    const float *q = xyz2 + (size_t)cloud * m * 3;
+    const int jbase = (blockIdx.x * kBQWarps + warp) * QPW;
+    // TMA bulk path needs the cloud base 16B aligned; tile starts are then aligned too (kBQTile*12 % 16 == 0)
+    const bool bulk = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+
+    float qx[QPW], qy[QPW], qz[QPW];
+    int cnt[QPW];
+    bool active = false;
+#pragma unroll
+    for (int t = 0; t < QPW; ++t) {
+        int j = jbase + t;
+        bool ok = j < m;
+        int jj = ok ? j : 0;
+        qx[t] = __ldg(q + 3 * jj); qy[t] = __ldg(q + 3 * jj + 1); qz[t] = __ldg(q + 3 * jj + 2);
+        cnt[t] = ok ? 0 : nsample;  // out-of-range queries are born finished
+        active |= ok;
+    }
+    int *myidx = widx + (size_t)warp * QPW * nsample;
+
+    const int ntiles = ceil_div(n, kBQTile);
+    if (bulk) {
+        if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
+    auto issue = [&](int t) {  // one thread: fetch tile t into buffer t&1
+        int cntp = min(kBQTile, n - t * kBQTile);
+        uint32_t bytes = (uint32_t)cntp * 12u;
+        uint32_t body = bytes & ~15u;
+        if (body) {
+            mbar_expect_tx(&full[t & 1], body);
+            bulk_g2s(tiles + (size_t)(t & 1) * kBQTile * 3, p + (size_t)t * kBQTile * 3, body, &full[t & 1]);
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[t & 1])) : "memory");
+        }
+    };
+    if (bulk && threadIdx.x == 0) issue(0);
+
+    int t = 0;
+    for (; t < ntiles; ++t) {
+        const int k0 = t * kBQTile;
+        const int cntp = min(kBQTile, n - k0);
+        float *tile = tiles + (size_t)(t & 1) * kBQTile * 3;
+        if (bulk) {
+            if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);  // buffer (t+1)&1 was released by the barrier closing tile t-1
+            mbar_wait(&full[t & 1], (t >> 1) & 1);
+            // the (<16 byte) tail the bulk engine cannot move
+            uint32_t bytes = (uint32_t)cntp * 12u, body = bytes & ~15u;
+            int tail0 = body >> 2, tail1 = bytes >> 2;
+            if (tail0 < tail1) {
+                if (threadIdx.x < tail1 - tail0) tile[tail0 + threadIdx.x] = __ldg(p + (size_t)k0 * 3 + tail0 + threadIdx.x);
+                __syncthreads();
+            }
+        } else {
+            for (int e = threadIdx.x; e < cntp * 3; e += kBQThreads) tile[e] = __ldg(p + (size_t)k0 * 3 + e);
+            __syncthreads();
+        }
+        if (active) {
+            for (int base = 0; base < cntp; base += 32) {
+                int kl = base + lane;
+                bool valid = kl < cntp;
+                int ks = valid ? kl : 0;
+                float x = tile[3 * ks], y = tile[3 * ks + 1], z = tile[3 * ks + 2];
+                bool alldone = true;
+#pragma unroll
+                for (int u = 0; u < QPW; ++u) {
+                    if (cnt[u] < nsample) {  // warp-uniform
+                        float s = sqdist_fma(qx[u], qy[u], qz[u], x, y, z);
+                        bool hit = valid && !(s > s_max);
+                        unsigned bal = __ballot_sync(GSPN_FULL_MASK, hit);
+                        if (bal) {
+                            int pos = cnt[u] + __popc(bal & ((1u << lane) - 1u));
+                            if (hit && pos < nsample) myidx[u * nsample + pos] = k0 + kl;
+                            cnt[u] = min(nsample, cnt[u] + __popc(bal));
+                        }
+                        alldone &= (cnt[u] >= nsample);
+                    }
+                }
+                if (alldone) { active = false; break; }
+            }
+        }
+        // tile buffer reuse + CTA-wide early exit once every warp has filled all its rows
+        if (__syncthreads_or(active ? 1 : 0) == 0) {
+            break;
+        }
+    }
+    // drain: when the CTA left early, tile t+1 was already requested; it must land before the CTA retires
+    if (bulk && t + 1 < ntiles) mbar_wait(&full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        int j = jbase + u;
+        if (j >= m) continue;
+        int cn = cnt[u];
+        int first = cn > 0 ? myidx[u * nsample] : 0;  // zero-hit row: zeros (reference leaves it unwritten)
+        __syncwarp();
+        for (int l = lane; l < nsample; l += 32) {
+            int v = l < cn ? myidx[u * nsample + l] : first;  // back-fill with the first hit (:29-32)
+            myidx[u * nsample + l] = v;
+            idx[((size_t)cloud * m + j) * nsample + l] = v;
+        }
+        if (lane == 0) pts_cnt[(size_t)cloud * m + j] = cn;
+        __syncwarp();
+        if (g.grouped) write_group(g, n, m, nsample, cloud, j, myidx + u * nsample, xyz1, qx[u], qy[u], qz[u], lane);
+    }
+}
+
+}  // namespace gspn
+
+using namespace gspn;
+
+static int launch_ballquery(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
+                            GroupArgs g, cudaStream_t s) {
+    const float s_max = ball_threshold(radius);
+    // QPW: more queries per warp amortise the shared-memory reads, but need enough warps to fill 148 SMs
+    long warps1 = (long)b * m;
+    int qpw = warps1 >= 148L * 8 * 8 * 4 ? 4 : (warps1 >= 148L * 8 * 8 * 2 ? 2 : 1);
+    if ((size_t)qpw * nsample * 4 * kBQWarps > 96 * 1024) qpw = 1;
+    size_t smem = (size_t)2 * kBQTile * 3 * 4 + (size_t)kBQWarps * qpw * nsample * 4;
+    if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;
+    dim3 grid(ceil_div(m, kBQWarps * qpw), b);
+#define GSPN_BQ_LAUNCH(Q)                                                                                                       \
+    do {                                                                                                                        \
+        GSPN_CUDA_OK(cudaFuncSetAttribute(ballquery_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        ballquery_kernel<Q><<<grid, kBQThreads, smem, s>>>(n, m, s_max, nsample, xyz1, xyz2, idx, pts_cnt, g);                   \
+    } while (0)
+    if (qpw == 4) GSPN_BQ_LAUNCH(4);
+    else if (qpw == 2) GSPN_BQ_LAUNCH(2);
+    else GSPN_BQ_LAUNCH(1);
+#undef GSPN_BQ_LAUNCH
+    return check_launch();
+}
+
+extern "C" int gspn_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
+                                     int *pts_cnt, gspn_stream_t stream) {
+    GSPN_REQUIRE(radius > 0.f && nsample > 0);  // tf_grouping.cpp:101,104
+    GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && b <= 65535);  // :109-114
+    if (b == 0 || m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(xyz1); GSPN_REQUIRE_PTR(xyz2); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(pts_cnt);
+    GroupArgs g = {};
+    return launch_ballquery(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, g, as_stream(stream));
+}
+
+extern "C" size_t gspn_grouped_bytes(long rows, int c_plus_xyz, int grouped_dtype) {
+    if (rows <= 0 || c_plus_xyz <= 0) return 0;
+    if (grouped_dtype == GSPN_DT_BF16) {
+        long tiles = ceil_div_l(rows, kTileRows);
+        int ld = ceil_div(c_plus_xyz, 64) * 64;
+        return (size_t)tiles * (size_t)(ld / 64) * (size_t)kTileBytes;
+    }
+    return (size_t)rows * (size_t)c_plus_xyz * sizeof(float);
+}
+
+extern "C" int gspn_ballquery_group(int b, int n, int m, int c, float radius, int nsample, const float *xyz, const float *new_xyz,
+                                    const float *shift, const void *points, int points_dtype, int *idx, int *pts_cnt, void *grouped,
+                                    int grouped_dtype, int ld, gspn_stream_t stream) {
+    GSPN_REQUIRE(radius > 0.f && nsample > 0);
+    GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && b <= 65535);
+    if (points_dtype != GSPN_DT_F32 && points_dtype != GSPN_DT_BF16) return GSPN_E_BAD_DTYPE;
+    if (grouped_dtype != GSPN_DT_F32 && grouped_dtype != GSPN_DT_BF16) return GSPN_E_BAD_DTYPE;
+    if (b == 0 || m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(xyz); GSPN_REQUIRE_PTR(new_xyz); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(pts_cnt); GSPN_REQUIRE_PTR(grouped);
+    if (c > 0) GSPN_REQUIRE_PTR(points);
+    GSPN_REQUIRE(ld >= c + 3);
+    if (grouped_dtype == GSPN_DT_BF16) GSPN_REQUIRE(ld % 64 == 0);
+    GroupArgs g;
+    g.shift = shift;
+    g.points = points;
+    g.c = c;
+    g.points_bf16 = points_dtype == GSPN_DT_BF16;
+    g.grouped = grouped;
+    g.grouped_bf16 = grouped_dtype == GSPN_DT_BF16;
+    g.ld = ld;
+    return launch_ballquery(b, n, m, radius, nsample, xyz, new_xyz, idx, pts_cnt, g, as_stream(stream));
+}

@@ -1,0 +1,300 @@
+// fps.cu -- farthest point sampling (farthestpointsamplingKernel, tf_sampling_g.cu:105-170)
+// re-designed for B200.
+//
+// The reference keeps the running min-distance in a global scratch array, re-reads every point
+// past the first 3072 from global memory each round and reduces with a 9-step __syncthreads tree
+// on one CTA per cloud.  FPS is a chain of m-1 strictly sequential rounds, so what matters is the
+// latency of ONE round, not bandwidth.  Here a cloud is owned by a thread-block CLUSTER:
+//   * every thread keeps its PPT points (x,y,z) AND their running min-distance in registers for
+//     the whole kernel -- global memory is touched once (prologue) and for the m index stores;
+//   * per round: PPT fused distance updates, a thread-local argmax, two redux.sync per warp
+//     (max of the distance bits, then min of the tie-break key), one shared-memory hop per CTA,
+//     and one DSMEM all-to-all of the CTA winners (coordinates travel with the candidate, so the
+//     next round starts without a global load), closed by a cluster barrier.
+//
+// Bit-exactness with the reference: distances use its compiled rounding (common.cuh sqdist_fma);
+// its winner among equal maxima is the lowest (k mod 512, k) -- thread-strided scan with strict '>'
+// (:130,:146) + left-wins tree (:158).  The key  ((k&511)<<23)|(k>>9)  orders exactly like that,
+// independent of how points are mapped to threads here.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gspn {
+
+__device__ __forceinline__ unsigned fps_key(int k) { return ((unsigned)(k & 511) << 23) | ((unsigned)k >> 9); }
+__device__ __forceinline__ int fps_unkey(unsigned key) { return (int)(((key & 0x7FFFFFu) << 9) | (key >> 23)); }
+
+struct Cand {  // a candidate: squared distance bits, tie-break key, coordinates
+    int dbits;
+    unsigned key;
+    float x, y, z;
+};
+
+// warp-wide (max dist, then min key); every lane returns the winner's fields.
+__device__ __forceinline__ Cand warp_argmax(Cand c) {
+    int wm = __reduce_max_sync(GSPN_FULL_MASK, c.dbits);  // non-negative floats order as ints; -1.0f (empty) is negative
+    unsigned kk = (c.dbits == wm) ? c.key : 0xFFFFFFFFu;
+    unsigned wk = __reduce_min_sync(GSPN_FULL_MASK, kk);
+    int src = __ffs(__ballot_sync(GSPN_FULL_MASK, kk == wk)) - 1;
+    Cand r;
+    r.dbits = wm;
+    r.key = wk;
+    r.x = __shfl_sync(GSPN_FULL_MASK, c.x, src);
+    r.y = __shfl_sync(GSPN_FULL_MASK, c.y, src);
+    r.z = __shfl_sync(GSPN_FULL_MASK, c.z, src);
+    return r;
+}
+
+// barrier.cluster with release/acquire at cluster scope: orders the DSMEM stores before it
+// against the loads after it without the gpu-scope fence cooperative_groups' sync() adds.
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+constexpr int kMaxWarps = 32;
+constexpr int kMaxCluster = 16;
+
+struct __align__(16) Slot { float x, y, z; int dbits; };
+
+// PPT points per thread in registers.  grid = (CLUSTER, b), cluster = (CLUSTER,1,1).
+// Requires (blockDim.x*CLUSTER) % 512 == 0 or PPT == 1 so that a thread's points have ascending keys.
+template <int PPT, int CLUSTER, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out) {
+    __shared__ Slot wslot[2][kMaxWarps];
+    __shared__ unsigned wkey[2][kMaxWarps];
+    __shared__ Slot cslot[2][kMaxCluster];
+    __shared__ unsigned ckey[2][kMaxCluster];
+
+    const int cloud = blockIdx.y;
+    unsigned rank = 0;
+    if (CLUSTER > 1) rank = cg::this_cluster().block_rank();
+    const int T = blockDim.x * CLUSTER;
+    const int gtid = rank * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float *p = xyz + (size_t)cloud * n * 3;
+
+    float px[PPT], py[PPT], pz[PPT], td[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        int k = gtid + j * T;
+        if (k < n) {
+            px[j] = __ldg(p + 3 * k); py[j] = __ldg(p + 3 * k + 1); pz[j] = __ldg(p + 3 * k + 2);
+            td[j] = 1e38f;  // tf_sampling_g.cu:118
+        } else {
+            px[j] = py[j] = pz[j] = 0.f;
+            td[j] = -1.0f;  // min(d,-1) = -1 never beats the initial best of -1 (:125)
+        }
+    }
+    float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
+    if (gtid == 0) out[(size_t)cloud * m] = 0;
+    if (CLUSTER > 1) cluster_barrier();  // every CTA of the cluster is resident before DSMEM traffic
+
+    for (int r = 1; r < m; ++r) {
+        const int par = r & 1;
+        float best = -1.0f;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            float d = sqdist_fma(px[j], py[j], pz[j], x1, y1, z1);
+            float t = fminf(d, td[j]);
+            td[j] = t;
+            if (t > best) { best = t; bj = j; }
+        }
+        Cand c;
+        c.dbits = __float_as_int(best);
+        c.key = fps_key(gtid + bj * T);
+        c.x = px[0]; c.y = py[0]; c.z = pz[0];
+#pragma unroll
+        for (int j = 1; j < PPT; ++j)
+            if (bj == j) { c.x = px[j]; c.y = py[j]; c.z = pz[j]; }
+        c = warp_argmax(c);
+        if (lane == 0) {
+            wslot[par][warp] = Slot{c.x, c.y, c.z, c.dbits};
+            wkey[par][warp] = c.key;
+        }
+        __syncthreads();
+        if (CLUSTER == 1 || warp == 0) {
+            Cand w;
+            if (lane < nwarps) {
+                Slot s = wslot[par][lane];
+                w.dbits = s.dbits; w.key = wkey[par][lane]; w.x = s.x; w.y = s.y; w.z = s.z;
+            } else {
+                w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
+            }
+            c = warp_argmax(w);
+        }
+        if (CLUSTER > 1) {
+            cg::cluster_group cl = cg::this_cluster();
+            if (warp == 0 && lane < CLUSTER) {  // lane L posts this CTA's winner into CTA L's table
+                Slot *rs = cl.map_shared_rank(&cslot[par][rank], lane);
+                unsigned *rk = cl.map_shared_rank(&ckey[par][rank], lane);
+                *rs = Slot{c.x, c.y, c.z, c.dbits};
+                *rk = c.key;
+            }
+            cluster_barrier();  // remote stores visible to every CTA of the cluster
+            Cand w;
+            if (lane < CLUSTER) {
+                Slot s = cslot[par][lane];
+                w.dbits = s.dbits; w.key = ckey[par][lane]; w.x = s.x; w.y = s.y; w.z = s.z;
+            } else {
+                w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
+            }
+            c = warp_argmax(w);
+        }
+        x1 = c.x; y1 = c.y; z1 = c.z;
+        if (gtid == 0) out[(size_t)cloud * m + r] = fps_unkey(c.key);
+    }
+    if (CLUSTER > 1) cluster_barrier();  // no CTA exits while a peer may still address its smem
+}
+
+// Fallback for clouds that do not fit the register-resident kernel: one CTA per cloud, points
+// re-read from global/L2 every round, running min-distance in caller workspace (b*n floats) --
+// the reference's own structure with the warp-level reduction above.
+__global__ void __launch_bounds__(1024, 1) fps_stream_kernel(int n, int m, const float *__restrict__ xyz, float *__restrict__ temp,
+                                                             int *__restrict__ out) {
+    __shared__ Slot wslot[2][kMaxWarps];
+    __shared__ unsigned wkey[2][kMaxWarps];
+    const int cloud = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const float *p = xyz + (size_t)cloud * n * 3;
+    float *td = temp + (size_t)cloud * n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) td[k] = 1e38f;
+    float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);
+    if (threadIdx.x == 0) out[(size_t)cloud * m] = 0;
+    for (int r = 1; r < m; ++r) {
+        const int par = r & 1;
+        Cand c;
+        float best = -1.0f;
+        c.key = fps_key(threadIdx.x); c.x = c.y = c.z = 0.f;
+        // blockDim.x is a multiple of 512, so k mod 512 is constant per thread and keys ascend with k
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1), z = __ldg(p + 3 * k + 2);
+            float d = sqdist_fma(x, y, z, x1, y1, z1);
+            float o = td[k];
+            float t = fminf(d, o);
+            if (t != o) td[k] = t;
+            if (t > best) { best = t; c.key = fps_key(k); c.x = x; c.y = y; c.z = z; }
+        }
+        c.dbits = __float_as_int(best);
+        c = warp_argmax(c);
+        if (lane == 0) {
+            wslot[par][warp] = Slot{c.x, c.y, c.z, c.dbits};
+            wkey[par][warp] = c.key;
+        }
+        __syncthreads();
+        Cand w;
+        if (lane < nwarps) {
+            Slot s = wslot[par][lane];
+            w.dbits = s.dbits; w.key = wkey[par][lane]; w.x = s.x; w.y = s.y; w.z = s.z;
+        } else {
+            w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
+        }
+        c = warp_argmax(w);
+        x1 = c.x; y1 = c.y; z1 = c.z;
+        if (threadIdx.x == 0) out[(size_t)cloud * m + r] = fps_unkey(c.key);
+    }
+}
+
+template <int PPT, int CLUSTER, int MAXT>
+static int launch_resident(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s) {
+    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT>;
+    if (CLUSTER > 8) GSPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CLUSTER, b, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out));
+    return GSPN_OK;
+}
+
+template <int PPT, int MAXT>
+static int dispatch_cluster(int cluster, int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s) {
+    switch (cluster) {
+        case 1: return launch_resident<PPT, 1, MAXT>(b, n, m, inp, out, threads, s);
+        case 2: return launch_resident<PPT, 2, MAXT>(b, n, m, inp, out, threads, s);
+        case 4: return launch_resident<PPT, 4, MAXT>(b, n, m, inp, out, threads, s);
+        case 8: return launch_resident<PPT, 8, MAXT>(b, n, m, inp, out, threads, s);
+        case 16: return launch_resident<PPT, 16, MAXT>(b, n, m, inp, out, threads, s);
+    }
+    return GSPN_E_UNSUPPORTED;
+}
+
+static int launch_cfg(int b, int n, int m, const float *inp, int *out, int threads, int ppt, int cluster, cudaStream_t s) {
+    if (threads < 32 || threads > 1024 || threads % 32) return GSPN_E_UNSUPPORTED;
+    if (ppt > 1 && (threads * cluster) % 512) return GSPN_E_UNSUPPORTED;  // ascending keys per thread
+    if ((long)threads * ppt * cluster < n) return GSPN_E_UNSUPPORTED;
+    if (b > 65535) return GSPN_E_UNSUPPORTED;
+    switch (ppt) {
+        case 1: return dispatch_cluster<1, 1024>(cluster, b, n, m, inp, out, threads, s);
+        case 2: return dispatch_cluster<2, 1024>(cluster, b, n, m, inp, out, threads, s);
+        case 4: return dispatch_cluster<4, 1024>(cluster, b, n, m, inp, out, threads, s);
+        case 8: return dispatch_cluster<8, 1024>(cluster, b, n, m, inp, out, threads, s);
+        case 16: return threads <= 512 ? dispatch_cluster<16, 512>(cluster, b, n, m, inp, out, threads, s) : GSPN_E_UNSUPPORTED;
+        case 32: return threads <= 256 ? dispatch_cluster<32, 256>(cluster, b, n, m, inp, out, threads, s) : GSPN_E_UNSUPPORTED;
+    }
+    return GSPN_E_UNSUPPORTED;
+}
+
+// (threads, ppt, cluster) by cloud size; see DESIGN.md "FPS" for the measurements behind the table.
+static void choose_cfg(int n, int *threads, int *ppt, int *cluster) {
+    if (n <= 512) { *threads = ((n + 31) / 32) * 32; *ppt = 1; *cluster = 1; return; }
+    if (n <= 1024) { *threads = 512; *ppt = 2; *cluster = 1; return; }
+    if (n <= 2048) { *threads = 512; *ppt = 4; *cluster = 1; return; }
+    if (n <= 4096) { *threads = 1024; *ppt = 4; *cluster = 1; return; }
+    if (n <= 8192) { *threads = 1024; *ppt = 4; *cluster = 2; return; }
+    if (n <= 16384) { *threads = 1024; *ppt = 4; *cluster = 4; return; }
+    if (n <= 32768) { *threads = 1024; *ppt = 4; *cluster = 8; return; }
+    if (n <= 65536) { *threads = 1024; *ppt = 8; *cluster = 8; return; }
+    *threads = 512; *ppt = 16; *cluster = 16;  // up to 131072
+}
+
+constexpr int kMaxResident = 512 * 16 * 16;
+
+}  // namespace gspn
+
+using namespace gspn;
+
+extern "C" int gspn_fps_max_resident_points(void) { return kMaxResident; }
+
+extern "C" size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m) {
+    (void)m;
+    if (n <= kMaxResident || b <= 0) return 0;
+    return sizeof(float) * (size_t)b * (size_t)n;
+}
+
+extern "C" int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *out, int threads, int ppt, int cluster,
+                                              gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m > 0);  // npoint>0 tf_sampling.cpp:99; rank/shape :105
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out);
+    int t0, p0, c0;
+    choose_cfg(n, &t0, &p0, &c0);
+    if (threads <= 0) threads = t0;
+    if (ppt <= 0) ppt = p0;
+    if (cluster <= 0) cluster = c0;
+    int rc = launch_cfg(b, n, m, inp, out, threads, ppt, cluster, as_stream(stream));
+    if (rc != GSPN_OK) return rc;
+    return check_launch();
+}
+
+extern "C" int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
+                                          gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m > 0);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out);
+    if (n <= kMaxResident) return gspn_farthest_point_sample_cfg(b, n, m, inp, out, 0, 0, 0, stream);
+    size_t need = gspn_farthest_point_sample_workspace_bytes(b, n, m);
+    if (workspace == nullptr || workspace_bytes < need) return GSPN_E_WORKSPACE;
+    fps_stream_kernel<<<b, 1024, 0, as_stream(stream)>>>(n, m, inp, (float *)workspace, out);
+    return check_launch();
+}

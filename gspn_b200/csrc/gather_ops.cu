@@ -1,0 +1,244 @@
+// gather_ops.cu -- the HBM-bound row movers of the SA/FP path: gather_point, group_point,
+// three_interpolate and the scatter-add backward ops.  One thread per 16-byte vector of the
+// output where channels allow it (coalesced 128-bit stores, gathered 128-bit loads); grids are
+// sized from the element count, not a fixed <<<b,256>>> like the reference.
+#include "common.cuh"
+
+namespace gspn {
+
+constexpr int kThreads = 256;
+
+static inline int blocks_for(long work) {
+    long blk = ceil_div_l(work, kThreads);
+    // grid-stride beyond ~32 waves of 148 SMs x 8 CTAs
+    const long cap = 148L * 8 * 32;
+    return (int)(blk < cap ? (blk > 0 ? blk : 1) : cap);
+}
+
+// ---- gather_point: out[b,j,:] = inp[b,idx[b,j],:]   (tf_sampling_g.cu:172-181) ----------
+template <typename V>
+__global__ void __launch_bounds__(kThreads) gather_rows_kernel(long total, int n, int m, int cv /* vectors per row */,
+                                                               const V *__restrict__ inp, const int *__restrict__ idx, V *__restrict__ out) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / cv;  // b*m + j
+        int l = (int)(e - row * cv);
+        long bi = row / m;
+        int a = __ldg(idx + row);
+        out[e] = __ldg(inp + (bi * n + a) * cv + l);
+    }
+}
+
+// ---- scatter-add of rows: dst[b,idx[b,j],:] += src[b,j,:]   (tf_sampling_g.cu:183-192) ----
+__global__ void __launch_bounds__(kThreads) scatter_rows_kernel(long total, int n, int m, int c, const float *__restrict__ src,
+                                                                const int *__restrict__ idx, float *__restrict__ dst) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / c;
+        int l = (int)(e - row * c);
+        long bi = row / m;
+        int a = __ldg(idx + row);
+        atomicAdd(dst + (bi * n + a) * c + l, __ldg(src + e));
+    }
+}
+__global__ void __launch_bounds__(kThreads) scatter_rows_v4_kernel(long total, int n, int m, int cv, const float4 *__restrict__ src,
+                                                                   const int *__restrict__ idx, float4 *__restrict__ dst) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / cv;
+        int l = (int)(e - row * cv);
+        long bi = row / m;
+        int a = __ldg(idx + row);
+        atomicAdd(dst + (bi * n + a) * cv + l, __ldg(src + e));  // red.global.add.v4.f32 (sm_90+)
+    }
+}
+
+// ---- three_interpolate: out[j,l] = (p[i1,l]*w1 + p[i2,l]*w2) + p[i3,l]*w3, no FMA
+// (tf_interpolate.cpp:107-127) -------------------------------------------------------------
+__device__ __forceinline__ float interp3(float a, float b, float c, float w1, float w2, float w3) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a, w1), __fmul_rn(b, w2)), __fmul_rn(c, w3));
+}
+
+__global__ void __launch_bounds__(kThreads) three_interpolate_v4_kernel(long total, int m, int n, int cv, const float4 *__restrict__ points,
+                                                                        const int *__restrict__ idx, const float *__restrict__ weight,
+                                                                        float4 *__restrict__ out) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / cv;  // b*n + j
+        int l = (int)(e - row * cv);
+        long bi = row / n;
+        const int *ip = idx + row * 3;
+        const float *wp = weight + row * 3;
+        int i1 = __ldg(ip), i2 = __ldg(ip + 1), i3 = __ldg(ip + 2);
+        float w1 = __ldg(wp), w2 = __ldg(wp + 1), w3 = __ldg(wp + 2);
+        const float4 *base = points + bi * m * cv + l;
+        float4 a = __ldg(base + (long)i1 * cv), b = __ldg(base + (long)i2 * cv), c = __ldg(base + (long)i3 * cv);
+        float4 o;
+        o.x = interp3(a.x, b.x, c.x, w1, w2, w3);
+        o.y = interp3(a.y, b.y, c.y, w1, w2, w3);
+        o.z = interp3(a.z, b.z, c.z, w1, w2, w3);
+        o.w = interp3(a.w, b.w, c.w, w1, w2, w3);
+        __stcs(out + e, o);  // streaming store: the interpolated map is read once by the MLP
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) three_interpolate_kernel(long total, int m, int n, int c, const float *__restrict__ points,
+                                                                     const int *__restrict__ idx, const float *__restrict__ weight,
+                                                                     float *__restrict__ out) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / c;
+        int l = (int)(e - row * c);
+        long bi = row / n;
+        const int *ip = idx + row * 3;
+        const float *wp = weight + row * 3;
+        const float *base = points + bi * m * c + l;
+        out[e] = interp3(__ldg(base + (long)__ldg(ip) * c), __ldg(base + (long)__ldg(ip + 1) * c), __ldg(base + (long)__ldg(ip + 2) * c),
+                         __ldg(wp), __ldg(wp + 1), __ldg(wp + 2));
+    }
+}
+
+// grad_points[i_t,l] += grad_out[j,l]*w_t   (tf_interpolate.cpp:131-153)
+__global__ void __launch_bounds__(kThreads) three_interpolate_grad_kernel(long total, int m, int n, int c, const float *__restrict__ grad_out,
+                                                                          const int *__restrict__ idx, const float *__restrict__ weight,
+                                                                          float *__restrict__ grad_points) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / c;
+        int l = (int)(e - row * c);
+        long bi = row / n;
+        const int *ip = idx + row * 3;
+        const float *wp = weight + row * 3;
+        float g = __ldg(grad_out + e);
+        float *base = grad_points + bi * m * c + l;
+        atomicAdd(base + (long)__ldg(ip) * c, __fmul_rn(g, __ldg(wp)));
+        atomicAdd(base + (long)__ldg(ip + 1) * c, __fmul_rn(g, __ldg(wp + 1)));
+        atomicAdd(base + (long)__ldg(ip + 2) * c, __fmul_rn(g, __ldg(wp + 2)));
+    }
+}
+
+// NnDistanceGrad, one direction (tf_nndistance_g.cu:132-151): g=2*grad*(p-q); p += g, q -= g.
+__global__ void __launch_bounds__(kThreads) nn_distance_grad_kernel(long total, int n, int m, const float *__restrict__ xyz1,
+                                                                    const float *__restrict__ xyz2, const float *__restrict__ grad_dist1,
+                                                                    const int *__restrict__ idx1, float *__restrict__ grad_xyz1,
+                                                                    float *__restrict__ grad_xyz2) {
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long bi = e / n;
+        int j2 = __ldg(idx1 + e);
+        const float *p = xyz1 + e * 3;
+        const float *q = xyz2 + (bi * m + j2) * 3;
+        float g = __fmul_rn(__ldg(grad_dist1 + e), 2.0f);
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            float v = __fmul_rn(g, __fsub_rn(__ldg(p + l), __ldg(q + l)));
+            atomicAdd(grad_xyz1 + e * 3 + l, v);
+            atomicAdd(grad_xyz2 + (bi * m + j2) * 3 + l, -v);
+        }
+    }
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace gspn
+
+using namespace gspn;
+
+extern "C" int gspn_gather_point(int b, int n, int m, int c, const float *inp, const int *idx, float *out, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && c > 0);  // tf_sampling.cpp:131-137
+    if (b == 0 || m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(out);
+    if (c % 4 == 0 && aligned16(inp) && aligned16(out)) {
+        long total = (long)b * m * (c / 4);
+        gather_rows_kernel<float4><<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, m, c / 4, (const float4 *)inp, idx, (float4 *)out);
+    } else {
+        long total = (long)b * m * c;
+        gather_rows_kernel<float><<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, m, c, inp, idx, out);
+    }
+    return check_launch();
+}
+
+extern "C" int gspn_gather_point_grad(int b, int n, int m, int c, const float *out_g, const int *idx, float *inp_g, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && c > 0);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(inp_g);
+    GSPN_CUDA_OK(cudaMemsetAsync(inp_g, 0, sizeof(float) * (size_t)b * n * c, as_stream(stream)));  // tf_sampling.cpp:174
+    if (m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(out_g); GSPN_REQUIRE_PTR(idx);
+    long total = (long)b * m * c;
+    scatter_rows_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, m, c, out_g, idx, inp_g);
+    return check_launch();
+}
+
+extern "C" int gspn_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0 && nsample > 0);  // tf_grouping.cpp:179-187
+    if (b == 0 || m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(points); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(out);
+    // a (b,m,nsample) index tensor is a (b, m*nsample) gather
+    long mk = (long)m * nsample;
+    GSPN_REQUIRE(mk < (1L << 31));
+    if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+        long total = (long)b * mk * (c / 4);
+        gather_rows_kernel<float4><<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, (int)mk, c / 4, (const float4 *)points, idx, (float4 *)out);
+    } else {
+        long total = (long)b * mk * c;
+        gather_rows_kernel<float><<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, (int)mk, c, points, idx, out);
+    }
+    return check_launch();
+}
+
+extern "C" int gspn_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx, float *grad_points,
+                                     gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0 && nsample > 0);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(grad_points);
+    GSPN_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * n * c, as_stream(stream)));  // tf_grouping.cpp:234
+    if (m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(grad_out); GSPN_REQUIRE_PTR(idx);
+    long mk = (long)m * nsample;
+    GSPN_REQUIRE(mk < (1L << 31));
+    if (c % 4 == 0 && aligned16(grad_out) && aligned16(grad_points)) {
+        long total = (long)b * mk * (c / 4);
+        scatter_rows_v4_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, (int)mk, c / 4, (const float4 *)grad_out, idx, (float4 *)grad_points);
+    } else {
+        long total = (long)b * mk * c;
+        scatter_rows_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, n, (int)mk, c, grad_out, idx, grad_points);
+    }
+    return check_launch();
+}
+
+extern "C" int gspn_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight, float *out,
+                                      gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && m > 0 && c > 0 && n >= 0);  // tf_interpolate.cpp:197-206
+    if (b == 0 || n == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(points); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(weight); GSPN_REQUIRE_PTR(out);
+    if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+        long total = (long)b * n * (c / 4);
+        three_interpolate_v4_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, m, n, c / 4, (const float4 *)points, idx, weight, (float4 *)out);
+    } else {
+        long total = (long)b * n * c;
+        three_interpolate_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, m, n, c, points, idx, weight, out);
+    }
+    return check_launch();
+}
+
+extern "C" int gspn_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight,
+                                           float *grad_points, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && m > 0 && c > 0 && n >= 0);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(grad_points);
+    GSPN_CUDA_OK(cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, as_stream(stream)));  // tf_interpolate.cpp:258
+    if (n == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(grad_out); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(weight);
+    long total = (long)b * n * c;
+    three_interpolate_grad_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, m, n, c, grad_out, idx, weight, grad_points);
+    return check_launch();
+}
+
+extern "C" int gspn_nn_distance_grad(int b, int n, int m, const float *xyz1, const float *xyz2, const float *grad_dist1, const int *idx1,
+                                     const float *grad_dist2, const int *idx2, float *grad_xyz1, float *grad_xyz2, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m > 0);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(xyz1); GSPN_REQUIRE_PTR(xyz2); GSPN_REQUIRE_PTR(grad_dist1); GSPN_REQUIRE_PTR(idx1);
+    GSPN_REQUIRE_PTR(grad_dist2); GSPN_REQUIRE_PTR(idx2); GSPN_REQUIRE_PTR(grad_xyz1); GSPN_REQUIRE_PTR(grad_xyz2);
+    cudaStream_t s = as_stream(stream);
+    GSPN_CUDA_OK(cudaMemsetAsync(grad_xyz1, 0, sizeof(float) * (size_t)b * n * 3, s));  // tf_nndistance_g.cu:153-154
+    GSPN_CUDA_OK(cudaMemsetAsync(grad_xyz2, 0, sizeof(float) * (size_t)b * m * 3, s));
+    long t1 = (long)b * n, t2 = (long)b * m;
+    nn_distance_grad_kernel<<<blocks_for(t1), kThreads, 0, s>>>(t1, n, m, xyz1, xyz2, grad_dist1, idx1, grad_xyz1, grad_xyz2);
+    nn_distance_grad_kernel<<<blocks_for(t2), kThreads, 0, s>>>(t2, m, n, xyz2, xyz1, grad_dist2, idx2, grad_xyz2, grad_xyz1);
+    return check_launch();
+}

@@ -1,0 +1,308 @@
+"""The reference's custom-op surface (tf_ops/*/tf_*.py) on torch CUDA tensors.
+
+Same names, positional order and return tuples as the reference wrappers:
+
+  farthest_point_sample(npoint, inp) -> idx                  tf_ops/sampling/tf_sampling.py:48-56
+  gather_point(inp, idx) -> out                              tf_ops/sampling/tf_sampling.py:29-37
+  query_ball_point(radius, nsample, xyz1, xyz2) -> (idx, pts_cnt)   tf_ops/grouping/tf_grouping.py:8-20
+  group_point(points, idx) -> out                            tf_ops/grouping/tf_grouping.py:54-62
+  three_nn(xyz1, xyz2) -> (dist, idx)                        tf_ops/3d_interpolation/tf_interpolate.py:8-17
+  three_interpolate(points, idx, weight) -> out              tf_ops/3d_interpolation/tf_interpolate.py:19-28
+  nn_distance(xyz1, xyz2) -> (dist1, idx1, dist2, idx2)      tf_ops/nn_distance/tf_nndistance.py:14-24
+
+torch is the tensor container (device memory, streams, autograd tape); every op runs a
+hand-written sm_100a kernel through the C ABI in include/gspn_b200.h.  There is no
+fallback: CPU tensors or a missing library raise.  Index tensors are int32 like the
+reference's.  Gradients mirror the reference's registrations: GatherPoint, GroupPoint,
+ThreeInterpolate and NnDistance are differentiable w.r.t. their float inputs
+(tf_sampling.py:43, tf_grouping.py:63, tf_interpolate.py:29, tf_nndistance.py:31);
+FarthestPointSample, QueryBallPoint and ThreeNN are not (ops.NoGradient).
+Shape errors raise ValueError carrying the reference's OP_REQUIRES message.
+"""
+import torch
+
+from . import _lib
+from ._lib import GSPN_DT_BF16, GSPN_DT_F32, check
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def _cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: gspn_b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _cuda_i32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: gspn_b200 has no CPU path" % name)
+    if t.dtype != torch.int32:
+        raise TypeError("%s must be int32 (the reference's index dtype), got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------- sampling
+def farthest_point_sample(npoint, inp):
+    """inp (b,n,3) f32 -> (b,npoint) i32; bit-identical to farthestpointsamplingKernel."""
+    _req(npoint > 0, "FarthestPointSample expects positive npoint")
+    _req(inp.dim() == 3 and inp.shape[2] == 3, "FarthestPointSample expects (batch_size,num_points,3) inp shape")
+    inp = _cuda_f32(inp.detach(), "inp")
+    b, n, _ = inp.shape
+    out = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
+    L = _lib.lib()
+    wsb = L.gspn_farthest_point_sample_workspace_bytes(b, n, npoint)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=inp.device) if wsb else None
+    check(L.gspn_farthest_point_sample(b, n, npoint, _p(inp), _p(out), _p(ws), wsb, _stream()), "farthest_point_sample")
+    return out
+
+
+class _GatherPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, idx):
+        b, n, c = inp.shape
+        m = idx.shape[1]
+        out = torch.empty((b, m, c), dtype=torch.float32, device=inp.device)
+        check(_lib.lib().gspn_gather_point(b, n, m, c, _p(inp), _p(idx), _p(out), _stream()), "gather_point")
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, out_g):
+        (idx,) = ctx.saved_tensors
+        out_g = out_g.contiguous()
+        b, m, c = out_g.shape
+        inp_g = torch.empty((b, ctx.n, c), dtype=torch.float32, device=out_g.device)
+        check(_lib.lib().gspn_gather_point_grad(b, ctx.n, m, c, _p(out_g), _p(idx), _p(inp_g), _stream()), "gather_point_grad")
+        return inp_g, None
+
+
+def gather_point(inp, idx):
+    """inp (b,n,c) f32, idx (b,m) i32 -> (b,m,c).  (The reference op is c=3 only.)"""
+    _req(inp.dim() == 3, "GatherPoint expects (batch_size,num_points,3) inp shape")
+    _req(idx.dim() == 2 and idx.shape[0] == inp.shape[0], "GatherPoint expects (batch_size,num_result) idx shape")
+    return _GatherPoint.apply(_cuda_f32(inp, "inp"), _cuda_i32(idx, "idx"))
+
+
+# ----------------------------------------------------------------------------- grouping
+def query_ball_point(radius, nsample, xyz1, xyz2):
+    """xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32."""
+    _req(radius > 0, "QueryBallPoint expects positive radius")
+    _req(nsample > 0, "QueryBallPoint expects positive nsample")
+    _req(xyz1.dim() == 3 and xyz1.shape[2] == 3, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")
+    _req(xyz2.dim() == 3 and xyz2.shape[2] == 3, "QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")
+    xyz1, xyz2 = _cuda_f32(xyz1.detach(), "xyz1"), _cuda_f32(xyz2.detach(), "xyz2")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+    check(_lib.lib().gspn_query_ball_point(b, n, m, float(radius), nsample, _p(xyz1), _p(xyz2), _p(idx), _p(cnt), _stream()),
+          "query_ball_point")
+    return idx, cnt
+
+
+class _GroupPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        b, n, c = points.shape
+        _, m, k = idx.shape
+        out = torch.empty((b, m, k, c), dtype=torch.float32, device=points.device)
+        check(_lib.lib().gspn_group_point(b, n, c, m, k, _p(points), _p(idx), _p(out), _stream()), "group_point")
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        b, m, k, c = grad_out.shape
+        g = torch.empty((b, ctx.n, c), dtype=torch.float32, device=grad_out.device)
+        check(_lib.lib().gspn_group_point_grad(b, ctx.n, c, m, k, _p(grad_out), _p(idx), _p(g), _stream()), "group_point_grad")
+        return g, None
+
+
+def group_point(points, idx):
+    """points (b,n,c) f32, idx (b,m,nsample) i32 -> (b,m,nsample,c)."""
+    _req(points.dim() == 3, "GroupPoint expects (batch_size, num_points, channel) points shape")
+    _req(idx.dim() == 3 and idx.shape[0] == points.shape[0], "GroupPoint expects (batch_size, npoints, nsample) idx shape")
+    return _GroupPoint.apply(_cuda_f32(points, "points"), _cuda_i32(idx, "idx"))
+
+
+# ----------------------------------------------------------------------------- interpolation
+def three_nn(xyz1, xyz2, return_weight=False):
+    """xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) squared ascending, idx (b,n,3) i32.
+    return_weight=True (extension) also returns pointnet_fp_module's inverse-distance weights."""
+    _req(xyz1.dim() == 3 and xyz1.shape[2] == 3, "ThreeNN expects (b,n,3) xyz1 shape.")
+    _req(xyz2.dim() == 3 and xyz2.shape[2] == 3 and xyz2.shape[0] == xyz1.shape[0], "ThreeNN expects (b,m,3) xyz2 shape.")
+    xyz1, xyz2 = _cuda_f32(xyz1.detach(), "xyz1"), _cuda_f32(xyz2.detach(), "xyz2")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
+    w = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device) if return_weight else None
+    check(_lib.lib().gspn_three_nn(b, n, m, _p(xyz1), _p(xyz2), _p(dist), _p(idx), _p(w), _stream()), "three_nn")
+    return (dist, idx, w) if return_weight else (dist, idx)
+
+
+class _ThreeInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, weight):
+        b, m, c = points.shape
+        n = idx.shape[1]
+        out = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
+        check(_lib.lib().gspn_three_interpolate(b, m, c, n, _p(points), _p(idx), _p(weight), _p(out), _stream()), "three_interpolate")
+        ctx.save_for_backward(idx, weight)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        b, n, c = grad_out.shape
+        g = torch.empty((b, ctx.m, c), dtype=torch.float32, device=grad_out.device)
+        check(_lib.lib().gspn_three_interpolate_grad(b, n, c, ctx.m, _p(grad_out), _p(idx), _p(weight), _p(g), _stream()),
+              "three_interpolate_grad")
+        return g, None, None  # tf_interpolate.py:34
+
+
+def three_interpolate(points, idx, weight):
+    """points (b,m,c), idx (b,n,3) i32, weight (b,n,3) -> (b,n,c)."""
+    _req(points.dim() == 3, "ThreeInterpolate expects (b,m,c) points shape")
+    _req(idx.dim() == 3 and idx.shape[0] == points.shape[0] and idx.shape[2] == 3, "ThreeInterpolate expects (b,n,3) idx shape")
+    _req(weight.dim() == 3 and tuple(weight.shape) == tuple(idx.shape), "ThreeInterpolate expects (b,n,3) weight shape")
+    return _ThreeInterpolate.apply(_cuda_f32(points, "points"), _cuda_i32(idx, "idx"), _cuda_f32(weight.detach(), "weight"))
+
+
+# ----------------------------------------------------------------------------- nn_distance
+class _NnDistance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, rounding):
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        dev = xyz1.device
+        d1 = torch.empty((b, n), dtype=torch.float32, device=dev)
+        i1 = torch.empty((b, n), dtype=torch.int32, device=dev)
+        d2 = torch.empty((b, m), dtype=torch.float32, device=dev)
+        i2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        check(_lib.lib().gspn_nn_distance(b, n, m, _p(xyz1), _p(xyz2), _p(d1), _p(i1), _p(d2), _p(i2), rounding, _stream()), "nn_distance")
+        ctx.save_for_backward(xyz1, xyz2, i1, i2)
+        ctx.mark_non_differentiable(i1, i2)
+        return d1, i1, d2, i2
+
+    @staticmethod
+    def backward(ctx, g1, _gi1, g2, _gi2):
+        xyz1, xyz2, i1, i2 = ctx.saved_tensors
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        g1 = torch.zeros((b, n), dtype=torch.float32, device=xyz1.device) if g1 is None else g1.contiguous()
+        g2 = torch.zeros((b, m), dtype=torch.float32, device=xyz1.device) if g2 is None else g2.contiguous()
+        gx1 = torch.empty_like(xyz1)
+        gx2 = torch.empty_like(xyz2)
+        check(_lib.lib().gspn_nn_distance_grad(b, n, m, _p(xyz1), _p(xyz2), _p(g1), _p(i1), _p(g2), _p(i2), _p(gx1), _p(gx2), _stream()),
+              "nn_distance_grad")
+        return gx1, gx2, None
+
+
+def nn_distance(xyz1, xyz2, rounding="cpu"):
+    """xyz1 (b,n,3), xyz2 (b,m,3) -> dist1 (b,n), idx1 (b,n) i32, dist2 (b,m), idx2 (b,m) i32.
+    rounding: 'cpu' = as the reference's CPU op rounds (the op TF-CPU runs), 'gpu' = as its
+    compiled CUDA kernel rounds.  Ties -> lowest index either way."""
+    _req(xyz1.dim() == 3, "NnDistance requires xyz1 be of shape (batch,#points,3)")
+    _req(xyz1.shape[2] == 3, "NnDistance only accepts 3d point set xyz1")
+    _req(xyz2.dim() == 3, "NnDistance requires xyz2 be of shape (batch,#points,3)")
+    _req(xyz2.shape[2] == 3, "NnDistance only accepts 3d point set xyz2")
+    _req(xyz2.shape[0] == xyz1.shape[0], "NnDistance expects xyz1 and xyz2 have same batch size")
+    if rounding not in ("cpu", "gpu"):
+        raise ValueError("rounding must be 'cpu' or 'gpu'")
+    return _NnDistance.apply(_cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2"), 1 if rounding == "gpu" else 0)
+
+
+# ----------------------------------------------------------------------------- fused / engine-level ops
+def ballquery_group(radius, nsample, xyz, new_xyz, points, grouped_dtype=torch.float32, shift=None):
+    """Fused query_ball_point + group_point(xyz) - new_xyz + group_point(points) + concat
+    (utils/pointnet_util.py:40-48).  Returns (idx, pts_cnt, grouped, ld).
+
+    grouped rows are [features(c) | xyz-centre(3) | 0-pad]  (features FIRST; callers permute the
+    first layer's weight rows accordingly).  float32: a (b*m*nsample, ld=c+3) tensor; bfloat16:
+    the 128B-swizzled tile image for mlp_chain (uint8 buffer), ld = 64*ceil((c+3)/64)."""
+    _req(radius > 0, "QueryBallPoint expects positive radius")
+    _req(nsample > 0, "QueryBallPoint expects positive nsample")
+    xyz, new_xyz = _cuda_f32(xyz.detach(), "xyz"), _cuda_f32(new_xyz.detach(), "new_xyz")
+    b, n, _ = xyz.shape
+    m = new_xyz.shape[1]
+    c = 0
+    pdt = GSPN_DT_F32
+    if points is not None:
+        if points.dtype == torch.bfloat16:
+            pdt = GSPN_DT_BF16
+            points = points.detach().contiguous()
+        else:
+            points = _cuda_f32(points.detach(), "points")
+        c = points.shape[2]
+    if shift is not None:
+        shift = _cuda_f32(shift.detach(), "shift")
+    L = _lib.lib()
+    rows = b * m * nsample
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz.device)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
+    if grouped_dtype == torch.bfloat16:
+        gdt = GSPN_DT_BF16
+        ld = ((c + 3 + 63) // 64) * 64
+        nbytes = L.gspn_grouped_bytes(rows, c + 3, gdt)
+        grouped = torch.empty((nbytes,), dtype=torch.uint8, device=xyz.device)
+        if rows % 128:
+            grouped[-(ld // 64) * 16384:].zero_()  # rows of the last tile that no query owns
+    else:
+        gdt = GSPN_DT_F32
+        ld = c + 3
+        grouped = torch.empty((rows, ld), dtype=torch.float32, device=xyz.device)
+    check(L.gspn_ballquery_group(b, n, m, c, float(radius), nsample, _p(xyz), _p(new_xyz), _p(shift), _p(points), pdt,
+                                 _p(idx), _p(cnt), _p(grouped), gdt, ld, _stream()), "ballquery_group")
+    return idx, cnt, grouped, ld
+
+
+def mlp_layer_f32(x, w, scale, shift, relu=True, pool=1):
+    """fp32 shared-MLP layer on CUDA cores: act((x@w)*scale+shift) [+ max over groups of `pool` rows].
+    x (rows,cin) f32 (row stride = x.stride(0)), w (cin,cout)."""
+    rows, cin = x.shape
+    cout = w.shape[1]
+    L = _lib.lib()
+    w, scale, shift = w.contiguous(), scale.contiguous(), shift.contiguous()
+    ldx = x.stride(0)
+    assert x.stride(1) == 1
+    if pool > 1 and (64 % pool == 0) and rows % pool == 0:
+        y = torch.empty((rows // pool, cout), dtype=torch.float32, device=x.device)
+        check(L.gspn_mlp_layer_f32(rows, cin, cout, _p(x), ldx, _p(w), _p(scale), _p(shift), int(relu), pool, _p(y), _stream()), "mlp_layer_f32")
+        return y
+    y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+    check(L.gspn_mlp_layer_f32(rows, cin, cout, _p(x), ldx, _p(w), _p(scale), _p(shift), int(relu), 1, _p(y), _stream()), "mlp_layer_f32")
+    if pool > 1:
+        z = torch.empty((rows // pool, cout), dtype=torch.float32, device=x.device)
+        check(L.gspn_max_pool_rows(rows // pool, pool, cout, _p(y), _p(z), _stream()), "max_pool_rows")
+        return z
+    return y
+
+
+def mlp_pool(x, k):
+    """tf.reduce_max over groups of k consecutive rows: x (groups*k, c) f32 -> (groups, c)."""
+    x = _cuda_f32(x, "x")
+    rows, c = x.shape
+    assert rows % k == 0
+    y = torch.empty((rows // k, c), dtype=torch.float32, device=x.device)
+    check(_lib.lib().gspn_max_pool_rows(rows // k, k, c, _p(x), _p(y), _stream()), "max_pool_rows")
+    return y

@@ -1,0 +1,192 @@
+"""PointNet++ set-abstraction / feature-propagation modules with the reference's signatures.
+
+  sample_and_group(npoint, radius, nsample, xyz, points, tnet_spec=None, knn=False, use_xyz=True)
+      utils/pointnet_util.py:17-54
+  pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training,
+                     bn_decay, scope, bn=True, pooling='max', tnet_spec=None, knn=False, use_xyz=True)
+      utils/pointnet_util.py:85-139
+  pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, reuse=False)
+      utils/pointnet_util.py:142-174
+
+The reference builds a TF graph whose variables live in TF's variable store under `scope`.
+Here `scope` keys a `VariableStore` (a dict of per-layer tensors named like the TF variables:
+<scope>/conv<i>/{weights,biases,bn/gamma,bn/beta,bn/moving_mean,bn/moving_variance}); the first call
+under a scope creates the variables (Xavier-uniform weights, zero biases, identity BN) exactly as
+tf.get_variable would, later calls reuse them.  Two execution precisions share every index op:
+
+  precision='fp32' : reference-precision MLP on CUDA cores (parity tolerance 1e-5),
+  precision='bf16' : tcgen05 tensor-core MLP chain fed by the fused ball-query+group tile image.
+
+Not built: is_training=True (batch-statistics BN + backward), knn=True,
+tnet_spec (undefined `tnet` in the reference itself, pointnet_util.py:44), pooling other than
+'max' (no call site in the model).  Those raise NotImplementedError instead of approximating.
+"""
+import math
+
+import torch
+
+from . import ops
+
+BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (utils/tf_util.py:530-534)
+
+DEFAULT_PRECISION = "fp32"
+
+
+class VariableStore(dict):
+    """scope -> list of layer dicts; the analogue of TF's global variable store."""
+
+    def __init__(self, device="cuda", seed=0):
+        super().__init__()
+        self.device = device
+        self.gen = torch.Generator(device="cpu")
+        self.gen.manual_seed(seed)
+
+    def layers(self, scope, prefix, cin, widths, bn):
+        key = "%s/%s" % (scope, prefix)
+        if key not in self:
+            made = []
+            c = cin
+            for cout in widths:
+                # tf.contrib.layers.xavier_initializer (uniform) on a [1,1,cin,cout] kernel (tf_util.py:29-33,162-167)
+                lim = math.sqrt(6.0 / (c + cout))
+                w = (torch.rand((c, cout), generator=self.gen, dtype=torch.float32) * 2 - 1) * lim
+                layer = {"weights": w.to(self.device), "biases": torch.zeros(cout, device=self.device)}
+                if bn:
+                    layer.update(gamma=torch.ones(cout, device=self.device), beta=torch.zeros(cout, device=self.device),
+                                 moving_mean=torch.zeros(cout, device=self.device), moving_variance=torch.ones(cout, device=self.device))
+                made.append(layer)
+                c = cout
+            self[key] = made
+        got = self[key]
+        assert len(got) == len(widths) and (not got or got[0]["weights"].shape[0] == cin), \
+            "variables under scope %r were created with a different shape" % key
+        return got
+
+
+VARIABLES = VariableStore()
+
+
+def fold_layer(layer):
+    """conv bias + inference batch norm as one affine: y = (x@W)*scale + shift."""
+    if layer.get("gamma") is not None:
+        scale = layer["gamma"] / torch.sqrt(layer["moving_variance"] + BN_EPS)
+        shift = (layer["biases"] - layer["moving_mean"]) * scale + layer["beta"]
+    else:
+        scale = torch.ones_like(layer["biases"])
+        shift = layer["biases"]
+    return scale.contiguous(), shift.contiguous()
+
+
+def _check_unbuilt(is_training, knn=False, tnet_spec=None, pooling="max"):
+    if is_training:
+        raise NotImplementedError("is_training=True (batch-statistics BN + backward) is not built yet (SURVEY.md 8f rank 1)")
+    if knn:
+        raise NotImplementedError("knn=True has no call site in the reference model (SURVEY.md 2.1 row 2)")
+    if tnet_spec is not None:
+        raise NotImplementedError("tnet_spec: `tnet` is undefined in the reference (utils/pointnet_util.py:44)")
+    if pooling != "max":
+        raise NotImplementedError("pooling=%r has no call site in the reference model; only 'max' is built" % pooling)
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, tnet_spec=None, knn=False, use_xyz=True):
+    """Reference-shaped outputs (new_xyz, new_points (b,m,K,3+c) with xyz FIRST, idx, grouped_xyz),
+    composed from the 1:1 ops like utils/pointnet_util.py:36-48."""
+    _check_unbuilt(False, knn, tnet_spec)
+    new_xyz = ops.gather_point(xyz, ops.farthest_point_sample(npoint, xyz))
+    idx, _ = ops.query_ball_point(radius, nsample, xyz, new_xyz)
+    grouped_xyz = ops.group_point(xyz, idx) - new_xyz.unsqueeze(2)
+    if points is not None:
+        grouped_points = ops.group_point(points, idx)
+        new_points = torch.cat([grouped_xyz, grouped_points], dim=-1) if use_xyz else grouped_points
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def sample_and_group_all(xyz, points, use_xyz=True):
+    """utils/pointnet_util.py:57-82."""
+    b, n, _ = xyz.shape
+    new_xyz = torch.zeros((b, 1, 3), dtype=torch.float32, device=xyz.device)
+    idx = torch.arange(n, dtype=torch.int32, device=xyz.device).reshape(1, 1, n).repeat(b, 1, 1)
+    grouped_xyz = xyz.reshape(b, 1, n, 3)
+    if points is not None:
+        new_points = (torch.cat([xyz, points], dim=2) if use_xyz else points).unsqueeze(1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def _run_mlp_f32(x2d, layers, pool_last=1):
+    for i, layer in enumerate(layers):
+        scale, shift = fold_layer(layer)
+        pool = pool_last if i == len(layers) - 1 else 1
+        x2d = ops.mlp_layer_f32(x2d, layer["weights"], scale, shift, relu=True, pool=pool)
+    return x2d
+
+
+def _features_first(w, c, use_xyz, has_points):
+    """Rows of the first-layer kernel re-ordered for the fused grouping layout [features | xyz].
+    Reference order is [xyz | features] (pointnet_util.py:48)."""
+    if not has_points:
+        return w  # rows are xyz only
+    if use_xyz:
+        return torch.cat([w[3:], w[:3]], dim=0).contiguous()
+    return torch.cat([w, torch.zeros((3, w.shape[1]), dtype=w.dtype, device=w.device)], dim=0)  # xyz columns ignored
+
+
+def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training, bn_decay, scope, bn=True,
+                       pooling="max", tnet_spec=None, knn=False, use_xyz=True, variables=None, precision=None):
+    """-> (new_xyz (b,m,3), new_points (b,m,mlp[-1] or mlp2[-1]), idx (b,m,nsample) int32)."""
+    _check_unbuilt(is_training, knn, tnet_spec, pooling)
+    store = VARIABLES if variables is None else variables
+    precision = precision or DEFAULT_PRECISION
+    b, n, _ = xyz.shape
+    c = 0 if points is None else points.shape[2]
+    cin = (3 + c if (use_xyz or points is None) else c)
+    layers = store.layers(scope, "conv", cin, list(mlp), bn)
+    layers2 = store.layers(scope, "conv_post_", mlp[-1] if mlp else cin, list(mlp2 or []), bn)
+
+    if group_all:
+        new_xyz, new_points, idx, _ = sample_and_group_all(xyz, points, use_xyz)
+        x = _run_mlp_f32(new_points.reshape(b * n, cin).contiguous(), layers)
+        x = ops.mlp_pool(x, n)
+        m = 1
+    else:
+        fps_idx = ops.farthest_point_sample(npoint, xyz)
+        new_xyz = ops.gather_point(xyz, fps_idx)
+        m = npoint
+        if precision == "bf16":
+            from . import mlp_tc
+            idx, x = mlp_tc.sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz)
+        else:
+            idx, _, grouped, _ = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
+            if layers:
+                first = dict(layers[0])
+                first["weights"] = _features_first(first["weights"], c, use_xyz, points is not None)
+                x = _run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
+            else:
+                x = ops.mlp_pool(grouped, nsample)
+    x = _run_mlp_f32(x, layers2)
+    return new_xyz, x.reshape(b, m, x.shape[-1]), idx
+
+
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, reuse=False, variables=None,
+                       precision=None):
+    """-> new_points1 (b,n,mlp[-1])  (or the concatenated (b,n,c2+c1) map when mlp == [])."""
+    _check_unbuilt(is_training)
+    store = VARIABLES if variables is None else variables
+    precision = precision or DEFAULT_PRECISION
+    b, n, _ = xyz1.shape
+    c2 = points2.shape[2]
+    c1 = 0 if points1 is None else points1.shape[2]
+    layers = store.layers(scope, "conv_", c1 + c2, list(mlp), bn)
+    _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
+    if precision == "bf16" and layers:
+        from . import mlp_tc
+        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers)
+    interpolated = ops.three_interpolate(points2, idx, weight)
+    new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
+    if not layers:
+        return new_points1
+    x = _run_mlp_f32(new_points1.reshape(b * n, c1 + c2), layers)
+    return x.reshape(b, n, x.shape[-1])

@@ -1,0 +1,175 @@
+/*
+ * gspn_b200.h -- C ABI of libgspn_b200.so: the PointNet++ set-abstraction /
+ * feature-propagation hot path of ericyi/GSPN as hand-written sm_100a CUDA.
+ *
+ * This is the boundary a maintainer of the reference would bind instead of the
+ * four TensorFlow op libraries (tf_sampling_so.so, tf_grouping_so.so,
+ * tf_interpolate_so.so, tf_nndistance_so.so).  Every entry point cites the
+ * reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers,
+ *     C-contiguous, channel-last, float32 / int32 exactly like the reference
+ *     tensors ((b,n,3), (b,n,c), (b,m,nsample), (b,m,nsample,c)).
+ *   - the caller owns every buffer (outputs and workspace); the library never
+ *     allocates, frees or keeps state between calls, and is re-entrant.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the
+ *     call returns without synchronising; it is CUDA-graph capturable.
+ *   - return value: GSPN_OK (0) or a negative GSPN_E_* code; nothing throws.
+ *     The checks mirror the reference's OP_REQUIRES shape/attr checks.
+ *   - backward entry points zero their own outputs on `stream` first, as the
+ *     reference's Compute() does with cudaMemset.
+ */
+#ifndef GSPN_B200_H_
+#define GSPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *gspn_stream_t; /* cudaStream_t */
+
+enum {
+    GSPN_OK = 0,
+    GSPN_E_BAD_SHAPE = -1,   /* OP_REQUIRES shape / attr check failed            */
+    GSPN_E_NULL_PTR = -2,    /* a required pointer is NULL                       */
+    GSPN_E_BAD_DTYPE = -3,   /* unknown GSPN_DT_* value                          */
+    GSPN_E_WORKSPACE = -4,   /* workspace missing or smaller than *_workspace_bytes */
+    GSPN_E_CUDA = -5,        /* cudaGetLastError() after the launch was not success */
+    GSPN_E_UNSUPPORTED = -6  /* valid request outside what this build implements */
+};
+
+enum { GSPN_DT_F32 = 0, GSPN_DT_BF16 = 1 };
+
+/* Human-readable text for a GSPN_E_* code (static storage). */
+const char *gspn_error_string(int code);
+/* ABI version: major*1000+minor. */
+int gspn_version(void);
+/* cudaGetErrorString of the last GSPN_E_CUDA seen by the calling thread. */
+const char *gspn_last_cuda_error(void);
+
+/* ------------------------------------------------------------------ sampling
+ * farthest_point_sample(npoint, inp)  tf_ops/sampling/tf_sampling.py:48-56
+ *   FarthestPointSampleGpuOp::Compute  tf_ops/sampling/tf_sampling.cpp:95-122
+ *   farthestpointsamplingLauncher(b,n,m,inp,temp,out)  tf_sampling_g.cu:203
+ * inp (b,n,3) f32 -> out (b,m) i32, bit-identical to the reference kernel
+ * (out[:,0]=0; ties -> lowest (k mod 512, k)).  The reference's temp (32,n)
+ * scratch is not needed when n <= gspn_fps_max_resident_points(); above that
+ * pass workspace of gspn_farthest_point_sample_workspace_bytes(b,n,m). */
+size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m);
+int gspn_fps_max_resident_points(void);
+int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out,
+                               void *workspace, size_t workspace_bytes, gspn_stream_t stream);
+/* Tuning door used by bench/tests: force (threads per CTA, points per thread,
+ * CTAs per cluster); 0 = choose.  Same results for every legal choice. */
+int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *out,
+                                   int threads, int ppt, int cluster, gspn_stream_t stream);
+
+/* gather_point(inp, idx)  tf_sampling.py:29-37; gatherpointLauncher tf_sampling_g.cu:206
+ * inp (b,n,c) , idx (b,m) -> out (b,m,c).  The reference is hard-wired to c=3;
+ * c is explicit here because the model also gathers colour (model_rpointnet.py:151). */
+int gspn_gather_point(int b, int n, int m, int c, const float *inp, const int *idx, float *out, gspn_stream_t stream);
+/* GatherPointGrad  tf_sampling.py:43-47; scatteraddpointLauncher tf_sampling_g.cu:209
+ * out_g (b,m,c), idx (b,m) -> inp_g (b,n,c) (zeroed here, then scatter-added). */
+int gspn_gather_point_grad(int b, int n, int m, int c, const float *out_g, const int *idx, float *inp_g, gspn_stream_t stream);
+
+/* ------------------------------------------------------------------ grouping
+ * query_ball_point(radius, nsample, xyz1, xyz2)  tf_ops/grouping/tf_grouping.py:8-20
+ *   queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)  tf_grouping_g.cu:186
+ * xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32.
+ * First nsample hits in index order, first hit back-fills the row; a row with
+ * no hit (unwritten by the reference) is zero. */
+int gspn_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
+                          int *idx, int *pts_cnt, gspn_stream_t stream);
+/* group_point(points, idx)  tf_grouping.py:54-62; groupPointLauncher tf_grouping_g.cu:194
+ * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */
+int gspn_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out, gspn_stream_t stream);
+/* GroupPointGrad  tf_grouping.py:63-67; groupPointGradLauncher tf_grouping_g.cu:198
+ * grad_out (b,m,nsample,c), idx -> grad_points (b,n,c) (zeroed here). */
+int gspn_group_point_grad(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx, float *grad_points, gspn_stream_t stream);
+
+/* Fused ball query + group (sample_and_group, utils/pointnet_util.py:40-48, and
+ * multi_encoding_net, models/model_rpointnet.py:53-61) in ONE kernel.
+ * Besides idx / pts_cnt it writes the neighbourhood rows
+ *     row(b,j,s) = [ points[b,idx,:c] | xyz[b,idx]-new_xyz[b,j]-shift[b,j] | 0.. ]   (features first)
+ * `points` may be NULL (c=0).  shift (b,m,3) may be NULL.  grouped_dtype selects
+ *   GSPN_DT_F32 : plain row-major (b*m*nsample, ld) float rows, ld >= c+3;
+ *   GSPN_DT_BF16: the tensor-core-ready tile image consumed by gspn_mlp_chain
+ *                 (128-row x 64-col bf16 blocks, 128B-swizzled, ld = 64*ceil((c+3)/64)).
+ * points_dtype is the dtype of `points` (f32 as in the reference, or bf16 as
+ * produced by gspn_mlp_chain). */
+size_t gspn_grouped_bytes(long rows, int c_plus_xyz, int grouped_dtype);
+int gspn_ballquery_group(int b, int n, int m, int c, float radius, int nsample,
+                         const float *xyz, const float *new_xyz, const float *shift,
+                         const void *points, int points_dtype,
+                         int *idx, int *pts_cnt, void *grouped, int grouped_dtype, int ld,
+                         gspn_stream_t stream);
+
+/* ------------------------------------------------------------- interpolation
+ * three_nn(xyz1, xyz2)  tf_ops/3d_interpolation/tf_interpolate.py:8-17; threenn_cpu tf_interpolate.cpp:60
+ * xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) squared f32 ascending, idx (b,n,3) i32.
+ * If weight != NULL also writes the inverse-distance weights of
+ * pointnet_fp_module (utils/pointnet_util.py:157-160) so no elementwise pass is needed. */
+int gspn_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight, gspn_stream_t stream);
+/* three_interpolate(points, idx, weight)  tf_interpolate.py:19-28; threeinterpolate_cpu tf_interpolate.cpp:107
+ * points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c); (p1*w1+p2*w2)+p3*w3 without FMA. */
+int gspn_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight, float *out, gspn_stream_t stream);
+/* ThreeInterpolateGrad  tf_interpolate.py:29-34; threeinterpolate_grad_cpu tf_interpolate.cpp:131
+ * grad_out (b,n,c) -> grad_points (b,m,c) (zeroed here). */
+int gspn_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points, gspn_stream_t stream);
+
+/* --------------------------------------------------------------- nn_distance
+ * nn_distance(xyz1, xyz2)  tf_ops/nn_distance/tf_nndistance.py:14-24
+ *   nnsearch tf_nndistance.cpp:21-43 (CPU op) / NmDistanceKernelLauncher tf_nndistance_g.cu:128 (GPU op)
+ * xyz1 (b,n,3), xyz2 (b,m,3) -> dist1 (b,n), idx1 (b,n), dist2 (b,m), idx2 (b,m).
+ * rounding: 0 = as the CPU op rounds (mul,mul,add,mul,add), 1 = as the compiled
+ * GPU kernel rounds (mul,fma,fma).  Ties -> lowest index in both. */
+int gspn_nn_distance(int b, int n, int m, const float *xyz1, const float *xyz2,
+                     float *dist1, int *idx1, float *dist2, int *idx2, int rounding, gspn_stream_t stream);
+/* NnDistanceGrad  tf_nndistance.py:31-37; tf_nndistance.cpp:126-163 / tf_nndistance_g.cu:152 */
+int gspn_nn_distance_grad(int b, int n, int m, const float *xyz1, const float *xyz2,
+                          const float *grad_dist1, const int *idx1, const float *grad_dist2, const int *idx2,
+                          float *grad_xyz1, float *grad_xyz2, gspn_stream_t stream);
+
+/* ---------------------------------------------------------------- shared MLP
+ * The per-point MLP of pointnet_sa_module / pointnet_fp_module
+ * (utils/pointnet_util.py:109-113,124 and :167-172): layers of
+ * tf_util.conv2d 1x1 + bias + batch_norm(inference) + ReLU (utils/tf_util.py:170-184,530-534),
+ * optionally followed by tf.reduce_max over groups of `pool` consecutive rows.
+ *
+ * fp32 reference-precision path (CUDA cores): one layer per call.
+ *   x (rows,cin) f32, w (cin,cout) f32 (the [1,1,Cin,Cout] TF kernel), scale/shift (cout)
+ *   y = act(x@w * scale + shift)  [bias and BN folded by the caller: scale=g/sqrt(v+eps),
+ *   shift=(bias-mean)*scale+beta];  pool>1 (a divisor of 64): y (rows/pool, cout) = max over each group. */
+int gspn_mlp_layer_f32(long rows, int cin, int cout, const float *x, int ldx, const float *w,
+                       const float *scale, const float *shift, int relu, int pool, float *y, gspn_stream_t stream);
+
+/* tf.reduce_max over groups of k consecutive rows: x (groups*k, c) -> y (groups, c)  (pointnet_util.py:124). */
+int gspn_max_pool_rows(long groups, int k, int c, const float *x, float *y, gspn_stream_t stream);
+
+/* bf16 tensor-core path (tcgen05 / TMEM), whole chain in one kernel.
+ *   a       : tile image from gspn_ballquery_group / gspn_fp_assemble (rows padded to 128)
+ *   nlayers : 1..4;  dims[0]=K0 (multiple of 64, as `ld` above), dims[l+1]=cout of layer l
+ *   wimg[l] : weight image from gspn_mlp_pack_weights; scale/shift as above (f32, cout_l)
+ *   pool    : 1 (no pooling) or a divisor of 128 (nsample) or a multiple of 128
+ *   out_f32 (rows/pool, cout_last) and/or out_bf16 (same shape, row-major bf16) may be NULL. */
+size_t gspn_mlp_weight_image_bytes(int cin_padded, int cout);
+int gspn_mlp_pack_weights(int cin, int cin_padded, int cout, const float *w_f32, const int *row_perm,
+                          void *wimg, gspn_stream_t stream);
+int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a,
+                   const void *const *wimg, const float *const *scale, const float *const *shift,
+                   const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream);
+
+/* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of
+ * points2 (b,m,c2) with idx/weight (b,n,3), concatenated with points1 (b,n,c1) (may be NULL, c1=0),
+ * written straight into the bf16 tile image (ld = 64*ceil((c1+c2)/64)) for gspn_mlp_chain. */
+int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float *points1, const float *points2,
+                     const int *idx, const float *weight, void *a_img, int ld, gspn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPN_B200_H_ */

@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports exactly what include/gspn_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+from gspn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "gspn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gspn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    assert os.path.dirname(_lib.LIB_PATH).startswith(ROOT)
+
+
+def test_every_declared_symbol_is_exported():
+    names = _declared()
+    assert len(names) >= 20
+    dll = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(dll, n)]
+    assert not missing, missing
+
+
+def test_binding_table_matches_header():
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_version_and_error_strings():
+    L = _lib.lib()
+    assert L.gspn_version() >= 1000
+    assert L.gspn_error_string(0) == b"ok"
+    for code in range(-6, 0):
+        assert L.gspn_error_string(code) != b"unknown error code"
+
+
+def test_argument_checks_need_no_gpu():
+    """Shape/attr validation happens before any CUDA call (OP_REQUIRES analogue)."""
+    L = _lib.lib()
+    assert L.gspn_farthest_point_sample(1, 0, 4, None, None, None, 0, None) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_farthest_point_sample(1, 8, 4, None, None, None, 0, None) == _lib.GSPN_E_NULL_PTR
+    assert L.gspn_query_ball_point(1, 8, 4, -1.0, 4, None, None, None, None, None) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_query_ball_point(1, 8, 4, 0.5, 0, None, None, None, None, None) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_nn_distance(1, 8, 8, None, None, None, None, None, None, 7, None) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_grouped_bytes(256, 6, _lib.GSPN_DT_BF16) == 2 * 16384
+    assert L.gspn_grouped_bytes(129, 67, _lib.GSPN_DT_BF16) == 2 * 2 * 16384
+
+
+def test_ops_refuse_cpu_tensors():
+    import pytest
+    import torch
+    import gspn_b200
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gspn_b200.farthest_point_sample(4, torch.zeros(1, 8, 3))
+    with pytest.raises(ValueError, match="FarthestPointSample expects positive npoint"):
+        gspn_b200.farthest_point_sample(0, torch.zeros(1, 8, 3))
+    with pytest.raises(ValueError, match="QueryBallPoint expects positive radius"):
+        gspn_b200.query_ball_point(0.0, 4, torch.zeros(1, 8, 3), torch.zeros(1, 2, 3))

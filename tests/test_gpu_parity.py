@@ -1,0 +1,419 @@
+"""Parity of the sm_100a kernels (through the C ABI) with the CPU oracle and, where the reference
+has a CUDA kernel, with that kernel itself (oracle/_ref/libref_gpu.so) -- same seeded inputs.
+
+Bars (BASELINE.json north_star): integer outputs (FPS / ball query / three_nn / nn_distance
+indices, gathered rows) bit-exact; three_interpolate bit-exact (same rounding as the CPU op);
+float MLP paths within the tolerance written in each test."""
+import numpy as np
+import pytest
+import torch
+
+import gspn_b200
+from gspn_b200 import _lib, ops, scenes
+from gspn_b200 import pointnet_util as pu
+
+import refgpu
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.int32)
+
+
+# ------------------------------------------------------------------------------------ FPS
+FPS_CASES = [
+    ("cfg1_cube", lambda: scenes.uniform_cube(1, 4096, seed=100), 1024),
+    ("cfg1_scene", lambda: scenes.scannet_like_batch(0, 1, 4096)[0], 1024),
+    ("dups", lambda: scenes.with_duplicates(scenes.uniform_cube(2, 3000, seed=5), 0.5), 700),
+    ("n5000_not_mult_512", lambda: scenes.uniform_cube(2, 5000, seed=6), 300),
+    ("tiny_n128", lambda: scenes.uniform_cube(3, 128, seed=7), 32),
+    ("n33", lambda: scenes.uniform_cube(2, 33, seed=8), 33),
+    ("b40_gridstride", lambda: scenes.uniform_cube(40, 300, seed=9), 20),
+    ("all_same_point", lambda: np.ones((1, 2000, 3), np.float32), 10),
+    ("m_gt_distinct", lambda: np.repeat(scenes.uniform_cube(1, 10, seed=10), 60, axis=1), 50),
+    ("n1", lambda: scenes.uniform_cube(2, 1, seed=11), 3),
+    ("sa2_2048", lambda: scenes.scannet_like_batch(5, 2, 2048)[0], 512),
+    ("n9000_cluster2", lambda: scenes.scannet_like_batch(7, 2, 9000)[0], 257),
+]
+
+
+@pytest.mark.parametrize("name,make,m", FPS_CASES, ids=[c[0] for c in FPS_CASES])
+def test_fps_bit_exact(cuda, oracle, name, make, m):
+    xyz = make()
+    got = N(gspn_b200.farthest_point_sample(m, T(xyz, cuda)))
+    assert got.dtype == np.int32
+    assert np.array_equal(got, oracle.farthest_point_sample(m, xyz))
+    if refgpu.available():
+        assert np.array_equal(got, N(refgpu.fps(m, T(xyz, cuda))))
+
+
+@pytest.mark.parametrize("threads,ppt,cluster", [(1024, 4, 1), (512, 8, 1), (512, 4, 2), (256, 4, 4), (512, 1, 8), (128, 4, 8),
+                                                 (256, 1, 16), (512, 16, 1), (256, 32, 2), (64, 8, 8)])
+def test_fps_every_mapping_gives_the_same_indices(cuda, oracle, threads, ppt, cluster):
+    xyz = scenes.with_duplicates(scenes.scannet_like_batch(11, 3, 4096)[0], 0.1)
+    exp = oracle.farthest_point_sample(200, xyz)
+    x = T(xyz, cuda)
+    out = torch.empty((3, 200), dtype=torch.int32, device=cuda)
+    rc = _lib.lib().gspn_farthest_point_sample_cfg(3, 4096, 200, x.data_ptr(), out.data_ptr(), threads, ppt, cluster,
+                                                   torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "fps_cfg")
+    assert np.array_equal(N(out), exp)
+
+
+def test_fps_full_size_config2(cuda, oracle):
+    """BASELINE config 2, SA1: 8 x 32768 -> 2048, against the oracle, the reference kernel and FPS properties."""
+    xyz = scenes.scannet_like_batch(0, 8, 32768)[0]
+    x = T(xyz, cuda)
+    got = N(gspn_b200.farthest_point_sample(2048, x))
+    assert (got[:, 0] == 0).all()
+    assert all(len(set(r)) == 2048 for r in got)
+    if refgpu.available():
+        assert np.array_equal(got, N(refgpu.fps(2048, x)))
+    assert np.array_equal(got[:2], oracle.farthest_point_sample(2048, xyz[:2]))
+    # property: the selected point's min-distance to the already selected set never increases
+    p = xyz[0][got[0]].astype(np.float64)
+    mind = np.full(2048, np.inf)
+    sel = []
+    for j in range(1, 2048):
+        mind = np.minimum(mind, ((p - p[j - 1]) ** 2).sum(1))
+        sel.append(mind[j])
+    assert all(a >= b * (1 - 1e-6) for a, b in zip(sel, sel[1:]))
+
+
+def test_fps_streaming_fallback_large_cloud(cuda, oracle):
+    n = gspn_b200._lib.lib().gspn_fps_max_resident_points() + 1000
+    xyz = scenes.uniform_cube(1, n, seed=12)
+    got = N(gspn_b200.farthest_point_sample(40, T(xyz, cuda)))
+    assert np.array_equal(got, oracle.farthest_point_sample(40, xyz))
+
+
+# ------------------------------------------------------------------------------------ gather / group
+@pytest.mark.parametrize("c", [3, 6, 64, 67])
+def test_gather_and_group_point_exact(cuda, oracle, c):
+    rng = np.random.RandomState(c)
+    pts = rng.randn(3, 500, c).astype(np.float32)
+    idx2 = rng.randint(0, 500, size=(3, 77)).astype(np.int32)
+    idx3 = rng.randint(0, 500, size=(3, 19, 8)).astype(np.int32)
+    assert np.array_equal(bits(N(gspn_b200.gather_point(T(pts, cuda), T(idx2, cuda)))), bits(oracle.gather_point(pts, idx2)))
+    got = N(gspn_b200.group_point(T(pts, cuda), T(idx3, cuda)))
+    assert np.array_equal(bits(got), bits(oracle.group_point(pts, idx3)))
+    if refgpu.available():
+        assert np.array_equal(bits(got), bits(N(refgpu.group_point(T(pts, cuda), T(idx3, cuda)))))
+
+
+# ------------------------------------------------------------------------------------ ball query
+BALL_CASES = [
+    ("cfg1_cube", lambda: scenes.uniform_cube(1, 4096, seed=100), 1024, 0.2, 32),
+    ("cfg1_scene", lambda: scenes.scannet_like_batch(1, 1, 4096)[0], 1024, 0.2, 32),
+    ("underfilled", lambda: scenes.uniform_cube(2, 2000, seed=13), 300, 0.05, 32),
+    ("dups", lambda: scenes.with_duplicates(scenes.uniform_cube(2, 2500, seed=14), 0.5), 400, 0.15, 16),
+    ("unaligned_clouds_n4097", lambda: scenes.uniform_cube(3, 4097, seed=15), 100, 0.2, 32),
+    ("k256_context", lambda: scenes.scannet_like_batch(2, 2, 8192)[0], 128, 0.5, 256),
+    ("k512_context", lambda: scenes.scannet_like_batch(2, 1, 8192)[0], 64, 1.5, 512),
+    ("k_not_mult_32", lambda: scenes.uniform_cube(2, 1000, seed=16), 50, 0.3, 20),
+    ("tiny", lambda: scenes.uniform_cube(2, 5, seed=17), 5, 0.5, 4),
+    ("b40", lambda: scenes.uniform_cube(40, 200, seed=18), 30, 0.3, 8),
+]
+
+
+@pytest.mark.parametrize("name,make,m,r,k", BALL_CASES, ids=[c[0] for c in BALL_CASES])
+def test_ball_query_bit_exact(cuda, oracle, name, make, m, r, k):
+    xyz = make()
+    fidx = oracle.farthest_point_sample(m, xyz)
+    q = oracle.gather_point(xyz, fidx)
+    idx, cnt = gspn_b200.query_ball_point(r, k, T(xyz, cuda), T(q, cuda))
+    eidx, ecnt = oracle.query_ball_point(r, k, xyz, q)
+    assert np.array_equal(N(cnt), ecnt) and np.array_equal(N(idx), eidx)
+    if refgpu.available():
+        ridx, rcnt = refgpu.query_ball_point(r, k, T(xyz, cuda), T(q, cuda))
+        assert np.array_equal(N(cnt), N(rcnt)) and np.array_equal(N(idx), N(ridx))
+
+
+def test_ball_query_zero_hit_rows_and_far_queries(cuda, oracle):
+    xyz = scenes.uniform_cube(2, 1000, seed=19)
+    q = np.concatenate([xyz[:, :10], np.full((2, 6, 3), 9.0, np.float32)], axis=1)
+    idx, cnt = gspn_b200.query_ball_point(0.1, 8, T(xyz, cuda), T(q, cuda))
+    eidx, ecnt = oracle.query_ball_point(0.1, 8, xyz, q)
+    assert np.array_equal(N(cnt), ecnt) and np.array_equal(N(idx), eidx)
+    assert (N(cnt)[:, 10:] == 0).all() and (N(idx)[:, 10:] == 0).all()
+
+
+def test_ball_query_radius_edge_uses_the_reference_predicate(cuda, oracle):
+    """Points at distance exactly r, just below and just above: sqrtf(s) < r decides, not s < r*r."""
+    r = np.float32(0.3)
+    base = np.zeros((1, 64, 3), np.float32)
+    up = dn = r
+    vals = [r]
+    for _ in range(31):
+        up = np.nextafter(up, np.float32(1), dtype=np.float32)
+        dn = np.nextafter(dn, np.float32(0), dtype=np.float32)
+        vals += [up, dn]
+    vals.append(np.float32(0.0))
+    base[0, :, 0] = np.array(vals[:64], np.float32)
+    q = np.zeros((1, 1, 3), np.float32)
+    idx, cnt = gspn_b200.query_ball_point(float(r), 64, T(base, cuda), T(q, cuda))
+    eidx, ecnt = oracle.query_ball_point(float(r), 64, base, q)
+    assert np.array_equal(N(cnt), ecnt) and np.array_equal(N(idx), eidx)
+
+
+def test_ball_query_full_size_config2_sa1(cuda, oracle):
+    xyz = scenes.scannet_like_batch(0, 8, 32768)[0]
+    x = T(xyz, cuda)
+    fidx = gspn_b200.farthest_point_sample(2048, x)
+    q = gspn_b200.gather_point(x, fidx)
+    idx, cnt = gspn_b200.query_ball_point(0.2, 32, x, q)
+    if refgpu.available():
+        ridx, rcnt = refgpu.query_ball_point(0.2, 32, x, q)
+        assert np.array_equal(N(cnt), N(rcnt)) and np.array_equal(N(idx), N(ridx))
+    eidx, ecnt = oracle.query_ball_point(0.2, 32, xyz[:1], N(q)[:1])
+    assert np.array_equal(N(cnt)[:1], ecnt) and np.array_equal(N(idx)[:1], eidx)
+    # size-independent properties: a query point is in its own ball; indices ascend up to cnt, then repeat idx[0]
+    i, c = N(idx), N(cnt)
+    assert (c >= 1).all()
+    asc = (np.diff(i, axis=2) > 0) | (np.arange(1, 32)[None, None, :] >= c[..., None])
+    assert asc.all()
+
+
+# ------------------------------------------------------------------------------------ fused ball query + group
+@pytest.mark.parametrize("c", [0, 3, 64, 67])
+def test_fused_ballquery_group_f32_and_bf16(cuda, oracle, c):
+    xyz, pts = scenes.uniform_cube(2, 1500, seed=20, channels=max(c, 1))
+    pts = pts if c else None
+    m, r, k = 96, 0.2, 32
+    q = oracle.gather_point(xyz, oracle.farthest_point_sample(m, xyz))
+    _, new_points, eidx, _ = oracle.sample_and_group(m, r, k, xyz, pts)  # (b,m,k,3+c) xyz first
+    exp = np.concatenate([new_points[..., 3:], new_points[..., :3]], axis=-1).reshape(2 * m * k, c + 3)  # features first
+    idx, cnt, grouped, ld = ops.ballquery_group(r, k, T(xyz, cuda), T(q, cuda), None if pts is None else T(pts, cuda), torch.float32)
+    assert np.array_equal(N(idx), eidx) and ld == c + 3
+    assert np.array_equal(bits(N(grouped)), bits(exp))
+    # bf16 tile image: decode the swizzle and compare with the bf16 rounding of the same rows
+    idx2, _, img, ld2 = ops.ballquery_group(r, k, T(xyz, cuda), T(q, cuda), None if pts is None else T(pts, cuda), torch.bfloat16)
+    assert np.array_equal(N(idx2), eidx) and ld2 % 64 == 0
+    dec = decode_tile_image(img, 2 * m * k, ld2)
+    want = torch.from_numpy(exp).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(dec[:, :c + 3], want) and (dec[:, c + 3:] == 0).all()
+
+
+def decode_tile_image(img, rows, ld):
+    """Inverse of common.cuh tile_chunk_offset: uint8 image -> (rows, ld) float32."""
+    raw = img.cpu().numpy().view(np.uint16)
+    r = np.arange(rows)[:, None]
+    ch = np.arange(ld // 8)[None, :]
+    off = ((r >> 7) * (ld // 64) + (ch >> 3)) * 16384 + ((r & 127) >> 3) * 1024 + (r & 7) * 128 + (((ch & 7) ^ (r & 7)) << 4)
+    el = (off[..., None] // 2 + np.arange(8)[None, None, :]).reshape(rows, ld)
+    u16 = raw[el]
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+# ------------------------------------------------------------------------------------ three_nn / interpolate
+NN_CASES = [
+    ("fp1", 8, 128, 32), ("fp3", 2, 2048, 512), ("ragged", 3, 1000, 257), ("m2", 2, 50, 2), ("m1", 1, 10, 1),
+    ("n_lt_block", 2, 5, 40), ("tile_tail", 1, 300, 1025),
+]
+
+
+@pytest.mark.parametrize("name,b,n,m", NN_CASES, ids=[c[0] for c in NN_CASES])
+def test_three_nn_bit_exact(cuda, oracle, name, b, n, m):
+    xyz1 = scenes.uniform_cube(b, n, seed=n)
+    xyz2 = scenes.with_duplicates(scenes.uniform_cube(b, m, seed=m + 1), 0.3) if m > 8 else scenes.uniform_cube(b, m, seed=m + 1)
+    k = min(n, m) // 2
+    xyz1[:, :k] = xyz2[:, :k]  # exact zero distances
+    dist, idx, w = gspn_b200.three_nn(T(xyz1, cuda), T(xyz2, cuda), return_weight=True)
+    ed, ei = oracle.three_nn(xyz1, xyz2)
+    assert np.array_equal(N(idx), ei)
+    assert np.array_equal(bits(N(dist)), bits(ed))
+    np.testing.assert_allclose(N(w), oracle.fp_weights(ed), rtol=1e-6, atol=0)  # tolerance: 1e-6 relative
+
+
+def test_three_nn_full_size_fp4(cuda, oracle):
+    """config 2 FP4: 32768 unknown vs 2048 known per cloud."""
+    xyz = scenes.scannet_like_batch(0, 2, 32768)[0]
+    known = oracle.gather_point(xyz, oracle.farthest_point_sample(2048, xyz))
+    dist, idx = gspn_b200.three_nn(T(xyz, cuda), T(known, cuda))
+    ed, ei = oracle.three_nn(xyz, known)
+    assert np.array_equal(N(idx), ei) and np.array_equal(bits(N(dist)), bits(ed))
+
+
+@pytest.mark.parametrize("c", [1, 37, 64, 128, 512])
+def test_three_interpolate_bit_exact(cuda, oracle, c):
+    rng = np.random.RandomState(c)
+    b, n, m = 2, 700, 90
+    pts = rng.randn(b, m, c).astype(np.float32)
+    idx = rng.randint(0, m, size=(b, n, 3)).astype(np.int32)
+    w = rng.rand(b, n, 3).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    got = N(gspn_b200.three_interpolate(T(pts, cuda), T(idx, cuda), T(w, cuda)))
+    assert np.array_equal(bits(got), bits(oracle.three_interpolate(pts, idx, w)))
+
+
+# ------------------------------------------------------------------------------------ nn_distance
+@pytest.mark.parametrize("b,n,m", [(2, 701, 1027), (1, 16, 2048), (3, 512, 512), (2, 5, 3), (1, 1, 1)])
+def test_nn_distance_both_roundings(cuda, oracle, b, n, m):
+    rng = np.random.RandomState(n + m)
+    a = rng.randn(b, n, 3).astype(np.float32)
+    c = rng.randn(b, m, 3).astype(np.float32)
+    k = min(n, m) // 2
+    c[:, :k] = a[:, :k]
+    for rounding, variant in (("cpu", False), ("gpu", True)):
+        got = [N(t) for t in gspn_b200.nn_distance(T(a, cuda), T(c, cuda), rounding=rounding)]
+        exp = oracle.nn_distance(a, c, gpu_variant=variant)
+        for g, e in zip(got, exp):
+            assert np.array_equal(bits(g), bits(e)), rounding
+    if refgpu.available():
+        got = [N(t) for t in gspn_b200.nn_distance(T(a, cuda), T(c, cuda), rounding="gpu")]
+        ref = [N(t) for t in refgpu.nn_distance(T(a, cuda), T(c, cuda))]
+        for g, e in zip(got, ref):
+            assert np.array_equal(bits(g), bits(e))
+
+
+# ------------------------------------------------------------------------------------ backward ops (atomics: tolerance)
+GRAD_TOL = dict(rtol=1e-4, atol=1e-4)  # the reference's own gradient tests use 1e-4 (tf_grouping_op_test.py:27)
+
+
+def test_backward_ops_match_oracle(cuda, oracle):
+    rng = np.random.RandomState(3)
+    # group_point grad through autograd, shapes of tf_grouping_op_test.py:11-16
+    pts = rng.rand(4, 256, 8).astype(np.float32)
+    xyz = rng.rand(4, 256, 3).astype(np.float32)
+    idx, _ = oracle.query_ball_point(0.3, 64, xyz, xyz[:, :32])
+    p = T(pts, cuda).requires_grad_(True)
+    out = gspn_b200.group_point(p, T(idx, cuda))
+    go = rng.randn(*out.shape).astype(np.float32)
+    out.backward(T(go, cuda))
+    np.testing.assert_allclose(N(p.grad), oracle.group_point_grad(pts, idx, go), **GRAD_TOL)
+    # gather_point grad
+    i2 = rng.randint(0, 256, size=(4, 50)).astype(np.int32)
+    x = T(xyz, cuda).requires_grad_(True)
+    o = gspn_b200.gather_point(x, T(i2, cuda))
+    g2 = rng.randn(*o.shape).astype(np.float32)
+    o.backward(T(g2, cuda))
+    np.testing.assert_allclose(N(x.grad), oracle.gather_point_grad(xyz, i2, g2), **GRAD_TOL)
+    # three_interpolate grad, shapes of tf_interpolate_op_test.py:8-13
+    pts2 = rng.rand(1, 8, 16).astype(np.float32)
+    x1 = rng.rand(1, 128, 3).astype(np.float32)
+    x2 = rng.rand(1, 8, 3).astype(np.float32)
+    _, ii = oracle.three_nn(x1, x2)
+    w = np.full((1, 128, 3), 1.0 / 3.0, np.float32)
+    pp = T(pts2, cuda).requires_grad_(True)
+    oo = gspn_b200.three_interpolate(pp, T(ii, cuda), T(w, cuda))
+    g3 = rng.randn(*oo.shape).astype(np.float32)
+    oo.backward(T(g3, cuda))
+    np.testing.assert_allclose(N(pp.grad), oracle.three_interpolate_grad(pts2, ii, w, g3), **GRAD_TOL)
+    # nn_distance grad
+    a = rng.randn(2, 300, 3).astype(np.float32)
+    c = rng.randn(2, 200, 3).astype(np.float32)
+    ta, tc = T(a, cuda).requires_grad_(True), T(c, cuda).requires_grad_(True)
+    d1, i1, d2, i2_ = gspn_b200.nn_distance(ta, tc)
+    gd1 = rng.randn(2, 300).astype(np.float32)
+    gd2 = rng.randn(2, 200).astype(np.float32)
+    (d1 * T(gd1, cuda)).sum().add((d2 * T(gd2, cuda)).sum()).backward()
+    e1, e2 = oracle.nn_distance_grad(a, c, gd1, N(i1), gd2, N(i2_))
+    np.testing.assert_allclose(N(ta.grad), e1, **GRAD_TOL)
+    np.testing.assert_allclose(N(tc.grad), e2, **GRAD_TOL)
+
+
+# ------------------------------------------------------------------------------------ shared MLP (fp32 path) and modules
+def rand_layers(rng, cin, widths, bn=True):
+    out = []
+    for co in widths:
+        lim = np.sqrt(6.0 / (cin + co))
+        layer = dict(weights=rng.uniform(-lim, lim, (cin, co)).astype(np.float32), biases=(rng.randn(co) * 0.1).astype(np.float32))
+        if bn:
+            layer.update(gamma=(rng.rand(co) + 0.5).astype(np.float32), beta=(rng.randn(co) * 0.1).astype(np.float32),
+                         moving_mean=(rng.randn(co) * 0.1).astype(np.float32), moving_variance=(rng.rand(co) + 0.5).astype(np.float32))
+        out.append(layer)
+        cin = co
+    return out
+
+
+def to_store(layers_np, key, dev):
+    st = pu.VariableStore(device=dev)
+    st[key] = [{k: T(v, dev) for k, v in l.items()} for l in layers_np]
+    return st
+
+
+MLP_F32_TOL = dict(rtol=1e-5, atol=1e-5)  # fp32 path vs fp32 oracle: only summation-order/FMA differences
+
+
+@pytest.mark.parametrize("rows,cin,cout,pool", [(1000, 6, 32, 1), (2048, 67, 64, 32), (640, 259, 512, 32), (4096, 131, 128, 1), (128, 16, 8, 64)])
+def test_mlp_layer_f32(cuda, oracle, rows, cin, cout, pool):
+    rng = np.random.RandomState(rows)
+    x = rng.randn(rows, cin).astype(np.float32)
+    layer = rand_layers(rng, cin, [cout])[0]
+    y = oracle.mlp_layer(x, layer)
+    if pool > 1:
+        y = y.reshape(rows // pool, pool, cout).max(1)
+    tl = {k: T(v, cuda) for k, v in layer.items()}
+    scale, shift = pu.fold_layer(tl)
+    got = N(ops.mlp_layer_f32(T(x, cuda), tl["weights"], scale, shift, relu=True, pool=pool))
+    np.testing.assert_allclose(got, y, **MLP_F32_TOL)
+
+
+def test_pointnet_sa_module_fp32_matches_oracle(cuda, oracle):
+    rng = np.random.RandomState(0)
+    xyz, col = scenes.scannet_like_batch(20, 2, 4096)
+    layers = rand_layers(rng, 6, [32, 32, 64])
+    st = to_store(layers, "layer1/conv", cuda)
+    st["layer1/conv_post_"] = []
+    nx, npts, idx = gspn_b200.pointnet_sa_module(T(xyz, cuda), T(col, cuda), npoint=512, radius=0.2, nsample=32, mlp=[32, 32, 64], mlp2=None,
+                                                 group_all=False, is_training=False, bn_decay=None, scope="layer1", variables=st,
+                                                 precision="fp32")
+    enx, enp, eidx = oracle.pointnet_sa_module(xyz, col, 512, 0.2, 32, [32, 32, 64], layers)
+    assert np.array_equal(N(idx), eidx) and np.array_equal(bits(N(nx)), bits(enx))
+    np.testing.assert_allclose(N(npts), enp, rtol=1e-4, atol=1e-5)
+
+
+def test_pointnet_sa_module_no_points_and_group_all(cuda, oracle):
+    rng = np.random.RandomState(1)
+    xyz = scenes.uniform_cube(2, 600, seed=3)
+    layers = rand_layers(rng, 3, [16, 32])
+    st = to_store(layers, "s/conv", cuda)
+    st["s/conv_post_"] = []
+    nx, npts, idx = gspn_b200.pointnet_sa_module(T(xyz, cuda), None, 64, 0.3, 16, [16, 32], None, False, False, None, "s", variables=st,
+                                                 precision="fp32")
+    enx, enp, eidx = oracle.pointnet_sa_module(xyz, None, 64, 0.3, 16, [16, 32], layers)
+    assert np.array_equal(N(idx), eidx)
+    np.testing.assert_allclose(N(npts), enp, rtol=1e-4, atol=1e-5)
+    # group_all (utils/pointnet_util.py:57-82): one region holding every point, xyz concatenated first
+    pts = rng.randn(2, 600, 5).astype(np.float32)
+    l2 = rand_layers(rng, 8, [16])
+    st2 = to_store(l2, "g/conv", cuda)
+    st2["g/conv_post_"] = []
+    gx, gp, gi = gspn_b200.pointnet_sa_module(T(xyz, cuda), T(pts, cuda), None, None, None, [16], None, True, False, None, "g", variables=st2,
+                                              precision="fp32")
+    exp = oracle.mlp_layer(np.concatenate([xyz, pts], axis=2), l2[0]).max(axis=1, keepdims=True)
+    assert (N(gx) == 0).all() and N(gi).shape == (2, 1, 600)
+    np.testing.assert_allclose(N(gp), exp, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("mlp,with_p1", [([256, 128], True), ([], True), ([64], False)])
+def test_pointnet_fp_module_fp32_matches_oracle(cuda, oracle, mlp, with_p1):
+    rng = np.random.RandomState(2)
+    xyz1 = scenes.scannet_like_batch(30, 2, 2048)[0]
+    xyz2 = oracle.gather_point(xyz1, oracle.farthest_point_sample(512, xyz1))
+    p1 = rng.randn(2, 2048, 64).astype(np.float32) if with_p1 else None
+    p2 = rng.randn(2, 512, 128).astype(np.float32)
+    cin = 128 + (64 if with_p1 else 0)
+    layers = rand_layers(rng, cin, mlp)
+    st = to_store(layers, "fa/conv_", cuda)
+    got = gspn_b200.pointnet_fp_module(T(xyz1, cuda), T(xyz2, cuda), None if p1 is None else T(p1, cuda), T(p2, cuda), mlp, False, None,
+                                       "fa", variables=st, precision="fp32")
+    exp = oracle.pointnet_fp_module(xyz1, xyz2, p1, p2, mlp, layers)
+    np.testing.assert_allclose(N(got), exp, rtol=1e-4, atol=1e-5)
+
+
+def test_unbuilt_variants_raise(cuda):
+    x = torch.zeros(1, 64, 3, device=cuda)
+    with pytest.raises(NotImplementedError):
+        gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], None, False, True, None, "t1")
+    with pytest.raises(NotImplementedError):
+        gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], None, False, False, None, "t2", pooling="avg")
