@@ -64,6 +64,7 @@ def build(verbose=False):
 
 
 _lib = None
+CALLS = [0]  # C-ABI compute calls that returned GSPN_OK (each enqueues >= 1 kernel); bench.py reports the delta
 
 
 def lib():
@@ -87,6 +88,7 @@ def check(code, what):
     """Map a GSPN_E_* return code to the exception the reference raises for the same mistake
     (errors::InvalidArgument -> ValueError; anything CUDA -> RuntimeError)."""
     if code == 0:
+        CALLS[0] += 1
         return
     l = lib()
     msg = l.gspn_error_string(code).decode()

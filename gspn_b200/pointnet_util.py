@@ -77,6 +77,22 @@ def fold_layer(layer):
     return scale.contiguous(), shift.contiguous()
 
 
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _Null()
+
+
+def _stage(timers, name):
+    """bench.py passes timers(name) -> context manager bracketing a stage with CUDA events."""
+    return timers(name) if timers is not None else _NULL
+
+
 def _check_unbuilt(is_training, knn=False, tnet_spec=None, pooling="max"):
     if is_training:
         raise NotImplementedError("is_training=True (batch-statistics BN + backward) is not built yet (SURVEY.md 8f rank 1)")
@@ -135,7 +151,7 @@ def _features_first(w, c, use_xyz, has_points):
 
 
 def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training, bn_decay, scope, bn=True,
-                       pooling="max", tnet_spec=None, knn=False, use_xyz=True, variables=None, precision=None):
+                       pooling="max", tnet_spec=None, knn=False, use_xyz=True, variables=None, precision=None, timers=None):
     """-> (new_xyz (b,m,3), new_points (b,m,mlp[-1] or mlp2[-1]), idx (b,m,nsample) int32)."""
     _check_unbuilt(is_training, knn, tnet_spec, pooling)
     store = VARIABLES if variables is None else variables
@@ -152,26 +168,30 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
         x = ops.mlp_pool(x, n)
         m = 1
     else:
-        fps_idx = ops.farthest_point_sample(npoint, xyz)
-        new_xyz = ops.gather_point(xyz, fps_idx)
+        with _stage(timers, scope + ":fps"):
+            fps_idx = ops.farthest_point_sample(npoint, xyz)
+        with _stage(timers, scope + ":gather"):
+            new_xyz = ops.gather_point(xyz, fps_idx)
         m = npoint
         if precision == "bf16":
             from . import mlp_tc
-            idx, x = mlp_tc.sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz)
+            idx, x = mlp_tc.sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz, store, scope, timers)
         else:
-            idx, _, grouped, _ = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
-            if layers:
-                first = dict(layers[0])
-                first["weights"] = _features_first(first["weights"], c, use_xyz, points is not None)
-                x = _run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
-            else:
-                x = ops.mlp_pool(grouped, nsample)
+            with _stage(timers, scope + ":ballquery_group"):
+                idx, _, grouped, _ = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
+            with _stage(timers, scope + ":mlp"):
+                if layers:
+                    first = dict(layers[0])
+                    first["weights"] = _features_first(first["weights"], c, use_xyz, points is not None)
+                    x = _run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
+                else:
+                    x = ops.mlp_pool(grouped, nsample)
     x = _run_mlp_f32(x, layers2)
     return new_xyz, x.reshape(b, m, x.shape[-1]), idx
 
 
 def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, reuse=False, variables=None,
-                       precision=None):
+                       precision=None, timers=None):
     """-> new_points1 (b,n,mlp[-1])  (or the concatenated (b,n,c2+c1) map when mlp == [])."""
     _check_unbuilt(is_training)
     store = VARIABLES if variables is None else variables
@@ -180,13 +200,16 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
     c2 = points2.shape[2]
     c1 = 0 if points1 is None else points1.shape[2]
     layers = store.layers(scope, "conv_", c1 + c2, list(mlp), bn)
-    _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
+    with _stage(timers, scope + ":three_nn"):
+        _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
     if precision == "bf16" and layers:
         from . import mlp_tc
-        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers)
-    interpolated = ops.three_interpolate(points2, idx, weight)
-    new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
+        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers)
+    with _stage(timers, scope + ":interpolate"):
+        interpolated = ops.three_interpolate(points2, idx, weight)
+        new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
     if not layers:
         return new_points1
-    x = _run_mlp_f32(new_points1.reshape(b * n, c1 + c2), layers)
+    with _stage(timers, scope + ":mlp"):
+        x = _run_mlp_f32(new_points1.reshape(b * n, c1 + c2), layers)
     return x.reshape(b, n, x.shape[-1])
