@@ -47,25 +47,78 @@ __device__ __forceinline__ Cand warp_argmax(Cand c) {
     return r;
 }
 
-// barrier.cluster with release/acquire at cluster scope: orders the DSMEM stores before it
-// against the loads after it without the gpu-scope fence cooperative_groups' sync() adds.
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t f_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared::cta address -> shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// asynchronous DSMEM stores that signal the destination CTA's mbarrier (complete_tx): no cluster barrier,
+// no gpu-scope fence on the round's critical path
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(a),
+                 "r"(b), "r"(c), "r"(d), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void f_mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void f_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FW_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FD_%=;\n\t"
+        "bra FW_%=;\n\t"
+        "FD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
 
 constexpr int kMaxWarps = 32;
-constexpr int kMaxCluster = 16;
+constexpr int kMaxCand = 128;  // CLUSTER * warps-per-CTA candidates per round in the all-to-all exchange
 
 struct __align__(16) Slot { float x, y, z; int dbits; };
 
+// argmax over a thread's PPT updated distances as a tournament (depth log2 PPT instead of a PPT-long
+// dependent chain); the left operand survives ties, so the lowest j -- the lowest key -- wins.
+template <int LO, int CNT>
+struct Tourney {
+    template <int PPT>
+    static __device__ __forceinline__ void run(const float (&t)[PPT], float &v, int &j) {
+        if constexpr (CNT == 1) {
+            v = t[LO];
+            j = LO;
+        } else {
+            float va, vb;
+            int ja, jb;
+            Tourney<LO, CNT / 2>::run(t, va, ja);
+            Tourney<LO + CNT / 2, CNT - CNT / 2>::run(t, vb, jb);
+            bool take = vb > va;
+            v = take ? vb : va;
+            j = take ? jb : ja;
+        }
+    }
+};
+
 // PPT points per thread in registers.  grid = (CLUSTER, b), cluster = (CLUSTER,1,1).
-// Requires (blockDim.x*CLUSTER) % 512 == 0 or PPT == 1 so that a thread's points have ascending keys.
+// Requires (blockDim.x*CLUSTER) % 512 == 0 or PPT == 1 so that a thread's points have ascending keys,
+// and CLUSTER * (blockDim.x/32) <= kMaxCand when CLUSTER > 1.
+// dynamic smem: float4 xyz copy, [PPT][blockDim.x], so only the round's winner lane fetches coordinates.
 template <int PPT, int CLUSTER, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out) {
-    __shared__ Slot wslot[2][kMaxWarps];
-    __shared__ unsigned wkey[2][kMaxWarps];
-    __shared__ Slot cslot[2][kMaxCluster];
-    __shared__ unsigned ckey[2][kMaxCluster];
+    extern __shared__ float4 sxyz[];
+    __shared__ Slot wslot[2][CLUSTER > 1 ? kMaxCand : kMaxWarps];
+    __shared__ unsigned wkey[2][CLUSTER > 1 ? kMaxCand : kMaxWarps];
+    __shared__ __align__(8) uint64_t xbar[2];
 
     const int cloud = blockIdx.y;
     unsigned rank = 0;
@@ -84,65 +137,75 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
             td[j] = 1e38f;  // tf_sampling_g.cu:118
         } else {
             px[j] = py[j] = pz[j] = 0.f;
-            td[j] = -1.0f;  // min(d,-1) = -1 never beats the initial best of -1 (:125)
+            td[j] = -1.0f;  // min(d,-1) = -1 never beats a real point (distances are >= 0)
         }
+        sxyz[j * blockDim.x + threadIdx.x] = make_float4(px[j], py[j], pz[j], 0.f);  // read back by this thread only
     }
     float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
     if (gtid == 0) out[(size_t)cloud * m] = 0;
-    if (CLUSTER > 1) cluster_barrier();  // every CTA of the cluster is resident before DSMEM traffic
+    const int ncand = CLUSTER * nwarps;
+    if (CLUSTER > 1) {
+        if (threadIdx.x == 0) {
+            f_mbar_init(f_smem_u32(&xbar[0]), 1);
+            f_mbar_init(f_smem_u32(&xbar[1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cluster_barrier();  // every CTA resident and its mbarriers initialised before any DSMEM traffic
+    }
 
     for (int r = 1; r < m; ++r) {
         const int par = r & 1;
-        float best = -1.0f;
-        int bj = 0;
+        if (CLUSTER > 1 && threadIdx.x == 0)  // this round's phase completes after ncand x (16+4) bytes have landed
+            f_mbar_expect_tx(f_smem_u32(&xbar[par]), (uint32_t)ncand * 20u);
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             float d = sqdist_fma(px[j], py[j], pz[j], x1, y1, z1);
-            float t = fminf(d, td[j]);
-            td[j] = t;
-            if (t > best) { best = t; bj = j; }
+            td[j] = fminf(d, td[j]);
         }
+        float best;
+        int bj;
+        Tourney<0, PPT>::run(td, best, bj);
         Cand c;
         c.dbits = __float_as_int(best);
         c.key = fps_key(gtid + bj * T);
-        c.x = px[0]; c.y = py[0]; c.z = pz[0];
-#pragma unroll
-        for (int j = 1; j < PPT; ++j)
-            if (bj == j) { c.x = px[j]; c.y = py[j]; c.z = pz[j]; }
-        c = warp_argmax(c);
-        if (lane == 0) {
-            wslot[par][warp] = Slot{c.x, c.y, c.z, c.dbits};
-            wkey[par][warp] = c.key;
-        }
-        __syncthreads();
-        if (CLUSTER == 1 || warp == 0) {
-            Cand w;
-            if (lane < nwarps) {
-                Slot s = wslot[par][lane];
-                w.dbits = s.dbits; w.key = wkey[par][lane]; w.x = s.x; w.y = s.y; w.z = s.z;
-            } else {
-                w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
+        // warp-level winner; its lane alone fetches the coordinates from the smem copy
+        int wm = __reduce_max_sync(GSPN_FULL_MASK, c.dbits);
+        unsigned kk = (c.dbits == wm) ? c.key : 0xFFFFFFFFu;
+        unsigned wk = __reduce_min_sync(GSPN_FULL_MASK, kk);
+        if (CLUSTER == 1) {
+            if (kk == wk) {
+                float4 q = sxyz[bj * blockDim.x + threadIdx.x];
+                wslot[par][warp] = Slot{q.x, q.y, q.z, wm};
+                wkey[par][warp] = wk;
             }
-            c = warp_argmax(w);
-        }
-        if (CLUSTER > 1) {
-            cg::cluster_group cl = cg::this_cluster();
-            if (warp == 0 && lane < CLUSTER) {  // lane L posts this CTA's winner into CTA L's table
-                Slot *rs = cl.map_shared_rank(&cslot[par][rank], lane);
-                unsigned *rk = cl.map_shared_rank(&ckey[par][rank], lane);
-                *rs = Slot{c.x, c.y, c.z, c.dbits};
-                *rk = c.key;
-            }
-            cluster_barrier();  // remote stores visible to every CTA of the cluster
-            Cand w;
+            __syncthreads();
+        } else {
+            // all-to-all: the winner's (x,y,z,d | key) goes straight into every CTA's table
+            const int src = __ffs(__ballot_sync(GSPN_FULL_MASK, kk == wk)) - 1;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane == src) q = sxyz[bj * blockDim.x + threadIdx.x];
+            q.x = __shfl_sync(GSPN_FULL_MASK, q.x, src);
+            q.y = __shfl_sync(GSPN_FULL_MASK, q.y, src);
+            q.z = __shfl_sync(GSPN_FULL_MASK, q.z, src);
             if (lane < CLUSTER) {
-                Slot s = cslot[par][lane];
-                w.dbits = s.dbits; w.key = ckey[par][lane]; w.x = s.x; w.y = s.y; w.z = s.z;
-            } else {
-                w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
+                const int slot = rank * nwarps + warp;
+                const uint32_t rbar = map_to_rank(f_smem_u32(&xbar[par]), lane);
+                st_async_v4(map_to_rank(f_smem_u32(&wslot[par][slot]), lane), __float_as_uint(q.x), __float_as_uint(q.y),
+                            __float_as_uint(q.z), (uint32_t)wm, rbar);
+                st_async_b32(map_to_rank(f_smem_u32(&wkey[par][slot]), lane), wk, rbar);
             }
-            c = warp_argmax(w);
+            f_mbar_wait(f_smem_u32(&xbar[par]), (uint32_t)(((r - 1) >> 1) & 1));  // barrier par serves rounds par, par+2, ...
         }
+        // every warp reduces the candidate table (<= kMaxCand entries, strided over the lanes)
+        const int cnt = CLUSTER == 1 ? nwarps : ncand;
+        Cand w;
+        w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
+        for (int i = lane; i < cnt; i += 32) {
+            Slot s = wslot[par][i];
+            unsigned k2 = wkey[par][i];
+            if (s.dbits > w.dbits || (s.dbits == w.dbits && k2 < w.key)) { w.dbits = s.dbits; w.key = k2; w.x = s.x; w.y = s.y; w.z = s.z; }
+        }
+        c = warp_argmax(w);
         x1 = c.x; y1 = c.y; z1 = c.z;
         if (gtid == 0) out[(size_t)cloud * m + r] = fps_unkey(c.key);
     }
@@ -204,7 +267,9 @@ static int launch_resident(int b, int n, int m, const float *inp, int *out, int 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER, b, 1);
     cfg.blockDim = dim3(threads, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    const size_t smem = sizeof(float4) * (size_t)PPT * threads;
+    if (smem > 48 * 1024) GSPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -233,6 +298,8 @@ static int launch_cfg(int b, int n, int m, const float *inp, int *out, int threa
     if (threads < 32 || threads > 1024 || threads % 32) return GSPN_E_UNSUPPORTED;
     if (ppt > 1 && (threads * cluster) % 512) return GSPN_E_UNSUPPORTED;  // ascending keys per thread
     if ((long)threads * ppt * cluster < n) return GSPN_E_UNSUPPORTED;
+    if (cluster > 1 && cluster * (threads / 32) > kMaxCand) return GSPN_E_UNSUPPORTED;  // all-to-all candidate table
+    if ((size_t)threads * ppt * 16 > 200 * 1024) return GSPN_E_UNSUPPORTED;
     if (b > 65535) return GSPN_E_UNSUPPORTED;
     switch (ppt) {
         case 1: return dispatch_cluster<1, 1024>(cluster, b, n, m, inp, out, threads, s);
@@ -250,12 +317,12 @@ static void choose_cfg(int n, int *threads, int *ppt, int *cluster) {
     if (n <= 512) { *threads = ((n + 31) / 32) * 32; *ppt = 1; *cluster = 1; return; }
     if (n <= 1024) { *threads = 512; *ppt = 2; *cluster = 1; return; }
     if (n <= 2048) { *threads = 512; *ppt = 4; *cluster = 1; return; }
-    if (n <= 4096) { *threads = 1024; *ppt = 4; *cluster = 1; return; }
-    if (n <= 8192) { *threads = 1024; *ppt = 4; *cluster = 2; return; }
-    if (n <= 16384) { *threads = 1024; *ppt = 4; *cluster = 4; return; }
-    if (n <= 32768) { *threads = 1024; *ppt = 4; *cluster = 8; return; }
-    if (n <= 65536) { *threads = 1024; *ppt = 8; *cluster = 8; return; }
-    *threads = 512; *ppt = 16; *cluster = 16;  // up to 131072
+    if (n <= 4096) { *threads = 512; *ppt = 8; *cluster = 1; return; }
+    if (n <= 8192) { *threads = 256; *ppt = 16; *cluster = 2; return; }
+    if (n <= 16384) { *threads = 256; *ppt = 16; *cluster = 4; return; }
+    if (n <= 32768) { *threads = 256; *ppt = 16; *cluster = 8; return; }
+    if (n <= 65536) { *threads = 256; *ppt = 32; *cluster = 8; return; }
+    *threads = 256; *ppt = 32; *cluster = 16;  // up to 131072 (non-portable cluster size)
 }
 
 constexpr int kMaxResident = 512 * 16 * 16;

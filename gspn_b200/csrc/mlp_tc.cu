@@ -1,12 +1,452 @@
-// mlp_tc.cu -- tcgen05 / TMEM shared-MLP chain (placeholder entry points until the kernel lands).
+// mlp_tc.cu -- the shared per-point MLP (+ max-pool over nsample) of pointnet_sa_module /
+// pointnet_fp_module (utils/pointnet_util.py:109-113,124,167-172; tf_util.conv2d 1x1 + bias + BN + ReLU,
+// utils/tf_util.py:170-184,530-534) as ONE tcgen05 kernel per module: the whole layer chain runs on a
+// 128-row tile without the activations ever leaving the SM.
+//
+//   * A operand (activations): 128 rows x K bf16, K-major, SWIZZLE_128B.  Layer 0 reads the tile image
+//     written by the fused ball-query+group kernel (or gspn_fp_assemble) -- each 128x64 block is one
+//     16 KiB cp.async.bulk (TMA bulk engine), no tensor map.  Layers >0 read what the previous
+//     layer's epilogue wrote into shared memory in the same swizzled layout.
+//   * B operand (weights): W^T as [cout x cin] bf16 K-major blocks, pre-swizzled once by
+//     gspn_mlp_pack_weights, streamed through a 4-stage shared-memory ring by cp.async.bulk with
+//     mbarrier complete_tx; the ring runs ahead across layers and tiles.
+//   * D accumulates in TMEM (fp32, 128 lanes x cout columns); tcgen05.mma kind::f16, M=128,
+//     N<=128 per instruction, issued by one thread; tcgen05.commit releases ring stages and signals
+//     the epilogue.
+//   * epilogue: tcgen05.ld 32x32b.x32 -> fp32 scale/shift (bias+BN folded) + ReLU -> bf16 ->
+//     swizzled st.shared (next layer's A) ; last layer: max over the nsample rows of a group with
+//     redux.sync on the (non-negative) float bits, coalesced fp32 / bf16 stores.
 #include "common.cuh"
-using namespace gspn;
-extern "C" size_t gspn_mlp_weight_image_bytes(int cin_padded, int cout) {
-    if (cin_padded <= 0 || cout <= 0 || cin_padded % 64) return 0;
-    return (size_t)(cin_padded / 64) * (size_t)((cout + 7) / 8 * 8) * 128;
+
+namespace gspn {
+
+constexpr int kMaxLayers = 4;
+constexpr int kTcThreads = 128;
+constexpr int kStages = 4;
+
+struct ChainParams {
+    long rows;
+    long ntiles;
+    int nlayers;
+    int K[kMaxLayers];  // padded input width (multiple of 64)
+    int N[kMaxLayers];  // output width (multiple of 32)
+    const unsigned char *wimg[kMaxLayers];
+    const float *scale[kMaxLayers];
+    const float *shift[kMaxLayers];
+    int relu[kMaxLayers];
+    const unsigned char *a;
+    int pool;
+    float *out_f32;
+    __nv_bfloat16 *out_bf16;
+    int nch;  // weight rows (output channels) per ring stage / per MMA
+    int tmem_cols;
+    uint32_t r0_bytes, r1_bytes, stage_bytes;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-extern "C" int gspn_mlp_pack_weights(int, int, int, const float *, const int *, void *, gspn_stream_t) { return GSPN_E_UNSUPPORTED; }
-extern "C" int gspn_mlp_chain(long, int, const int *, const void *, const void *const *, const float *const *, const float *const *,
-                              const int *, int, float *, void *, gspn_stream_t) { return GSPN_E_UNSUPPORTED; }
-extern "C" int gspn_fp_assemble(int, int, int, int, int, const float *, const float *, const int *, const float *, void *, int,
-                                gspn_stream_t) { return GSPN_E_UNSUPPORTED; }
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D_%=;\n\t"
+        "bra W_%=;\n\t"
+        "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major, 1), SBO>>4 = 1024>>4 [32,46), version 1 [46,48), layout 2 [61,64).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t instr_desc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+struct Cursor {  // position in the per-tile weight block sequence: layer, n-chunk, k-block
+    int l, nc, kb;
+    __device__ __forceinline__ void advance(const ChainParams &p) {
+        if (++kb == (p.K[l] >> 6)) {
+            kb = 0;
+            if (++nc == (p.N[l] + p.nch - 1) / p.nch) {
+                nc = 0;
+                if (++l == p.nlayers) l = 0;
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t raw = s_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
+    unsigned char *sm = smem_raw + (base - raw);
+    const uint32_t R[2] = {base, base + p.r0_bytes};
+    unsigned char *Rg[2] = {sm, sm + p.r0_bytes};
+    const uint32_t stg = base + p.r0_bytes + p.r1_bytes;
+    float *affine = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)kStages * p.stage_bytes);
+    const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kStages]), a_full = s_u32(&bars[2 * kStages]),
+                   mma_done = s_u32(&bars[2 * kStages + 1]);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2 * kStages + 2; ++i) mb_init(s_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
+    int aoff[kMaxLayers];
+    {
+        int o = 0;
+        for (int l = 0; l < p.nlayers; ++l) {
+            aoff[l] = o;
+            for (int i = tid; i < p.N[l]; i += kTcThreads) {
+                affine[o + i] = __ldg(p.scale[l] + i);
+                affine[o + p.N[l] + i] = __ldg(p.shift[l] + i);
+            }
+            o += 2 * p.N[l];
+        }
+    }
+    // zero both activation regions once: K padding columns must read as 0 for every tile
+    {
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 *r = reinterpret_cast<uint4 *>(sm);
+        for (uint32_t i = tid; i < (p.r0_bytes + p.r1_bytes) / 16; i += kTcThreads) r[i] = z;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    int blocks_per_tile = 0;
+    for (int l = 0; l < p.nlayers; ++l) blocks_per_tile += ((p.N[l] + p.nch - 1) / p.nch) * (p.K[l] >> 6);
+    long my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long total_blocks = my_tiles * blocks_per_tile;
+    long issued = 0, used = 0;  // weight blocks requested / consumed (thread 0 only)
+    Cursor ic = {0, 0, 0};
+    uint32_t a_par = 0, done_par = 0;
+    const int kb0 = p.K[0] >> 6;
+
+    for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if (tid == 0) {
+            mb_expect_tx(a_full, (uint32_t)kb0 * kTileBytes);
+            for (int kb = 0; kb < kb0; ++kb) bulk_load(R[0] + kb * kTileBytes, p.a + ((size_t)tile * kb0 + kb) * kTileBytes, kTileBytes, a_full);
+        }
+        for (int l = 0; l < p.nlayers; ++l) {
+            const uint32_t in = R[l & 1];
+            const int Nl = p.N[l], KBl = p.K[l] >> 6;
+            if (tid == 0) {
+                if (l == 0) { mb_wait(a_full, a_par); }
+                tc_fence_after();
+                const int nchunks = (Nl + p.nch - 1) / p.nch;
+                for (int nc = 0; nc < nchunks; ++nc) {
+                    const int nrows = min(p.nch, Nl - nc * p.nch);
+                    const uint32_t idesc = instr_desc(128, nrows);
+                    for (int kb = 0; kb < KBl; ++kb) {
+                        while (issued < total_blocks && issued < used + kStages) {  // keep the ring full
+                            const int s = (int)(issued % kStages);
+                            const long round = issued / kStages;
+                            if (round > 0) mb_wait(empty0 + 8 * s, (uint32_t)((round - 1) & 1));
+                            const int rows_i = min(p.nch, p.N[ic.l] - ic.nc * p.nch);
+                            const uint32_t bytes = (uint32_t)rows_i * 128u;
+                            mb_expect_tx(full0 + 8 * s, bytes);
+                            bulk_load(stg + s * p.stage_bytes,
+                                      p.wimg[ic.l] + (size_t)ic.kb * p.N[ic.l] * 128 + (size_t)ic.nc * p.nch * 128, bytes, full0 + 8 * s);
+                            ic.advance(p);
+                            ++issued;
+                        }
+                        const int s = (int)(used % kStages);
+                        mb_wait(full0 + 8 * s, (uint32_t)((used / kStages) & 1));
+                        tc_fence_after();
+                        const uint64_t ad = smem_desc(in + kb * kTileBytes), bd = smem_desc(stg + s * p.stage_bytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
+                            tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                        tc_commit(empty0 + 8 * s);  // stage free when these MMAs have read it
+                        ++used;
+                    }
+                }
+                tc_commit(mma_done);
+            }
+            __syncwarp();
+            mb_wait(mma_done, done_par);
+            done_par ^= 1;
+            tc_fence_after();
+
+            // ---- epilogue: thread = row (TMEM lane), 32 columns at a time
+            const bool last = (l == p.nlayers - 1);
+            const float *sc = affine + aoff[l], *sh = sc + Nl;
+            const int row = warp * 32 + lane;
+            const long grow = tile * kTileRows + row;
+            unsigned char *outb = Rg[(l + 1) & 1];
+            for (int c0 = 0; c0 < Nl; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = fmaf(__uint_as_float(v[i]), sc[c0 + i], sh[c0 + i]);
+                    f[i] = p.relu[l] ? fmaxf(x, 0.f) : x;
+                }
+                if (!last) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        int cc = (c0 >> 3) + g;  // 16-byte chunk index along K of the next layer
+                        uint4 pk = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                              pack2(f[8 * g + 6], f[8 * g + 7]));
+                        *reinterpret_cast<uint4 *>(outb + (size_t)(cc >> 3) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128 +
+                                                   (((cc & 7) ^ (row & 7)) << 4)) = pk;
+                    }
+                } else if (p.pool == 1) {
+                    if (grow < p.rows) {
+                        if (p.out_f32) {
+                            float4 *o = reinterpret_cast<float4 *>(p.out_f32 + grow * Nl + c0);
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) o[g] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                        }
+                        if (p.out_bf16) {
+                            uint4 *o = reinterpret_cast<uint4 *>(p.out_bf16 + grow * Nl + c0);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                o[g] = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                                  pack2(f[8 * g + 6], f[8 * g + 7]));
+                        }
+                    }
+                } else {
+                    // max over the 32 rows this warp holds: ReLU output is >= 0, so float order == int order
+                    int keep = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        int mx = __reduce_max_sync(GSPN_FULL_MASK, __float_as_int(f[i]));
+                        if (lane == i) keep = mx;
+                    }
+                    const long row0 = tile * kTileRows + warp * 32;
+                    if (row0 < p.rows) {
+                        const long grp = row0 / p.pool;
+                        if (p.pool == 32) {
+                            if (p.out_f32) p.out_f32[grp * Nl + c0 + lane] = __int_as_float(keep);
+                            if (p.out_bf16) p.out_bf16[grp * Nl + c0 + lane] = __float2bfloat16_rn(__int_as_float(keep));
+                        } else {
+                            atomicMax(reinterpret_cast<int *>(p.out_f32) + grp * Nl + c0 + lane, keep);  // out zeroed by the launcher
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();  // epilogue st.shared -> visible to the tensor core's async-proxy reads
+            __syncthreads();
+        }
+        a_par ^= 1;
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+}
+
+// ---- weights (cin,cout) f32 row-major -> [cin_padded/64] blocks of (cout x 64) bf16, K-major, 128B-swizzled
+__global__ void pack_weights_kernel(int cin, int cin_padded, int cout, const float *__restrict__ w, const int *__restrict__ row_perm,
+                                    unsigned char *__restrict__ img) {
+    long total = (long)cin_padded * cout;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        int k = (int)(e / cout), n = (int)(e - (long)k * cout);
+        int src = row_perm ? row_perm[k] : (k < cin ? k : -1);
+        float v = (src >= 0 && src < cin) ? w[(size_t)src * cout + n] : 0.f;
+        int kb = k >> 6, kk = k & 63;
+        size_t off = (size_t)kb * cout * 128 + (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(img + off) = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- FP front end: [three_interpolate(points2) | points1 | 0] -> bf16 tile image (one 16-byte chunk per thread)
+__global__ void __launch_bounds__(256) fp_assemble_kernel(long rows, int n, int m, int c1, int c2, const float *__restrict__ points1,
+                                                          const float *__restrict__ points2, const int *__restrict__ idx,
+                                                          const float *__restrict__ weight, unsigned char *__restrict__ img, int ld) {
+    const int chunks = ld >> 3;
+    const long total = rows * chunks;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        long row = e / chunks;
+        int ch = (int)(e - row * chunks);
+        long bi = row / n;
+        float v[8];
+        const int col0 = ch * 8;
+        if (col0 < c2) {
+            const int *ip = idx + row * 3;
+            const float *wp = weight + row * 3;
+            int i1 = __ldg(ip), i2 = __ldg(ip + 1), i3 = __ldg(ip + 2);
+            float w1 = __ldg(wp), w2 = __ldg(wp + 1), w3 = __ldg(wp + 2);
+            const float *b1 = points2 + (bi * m + i1) * c2, *b2 = points2 + (bi * m + i2) * c2, *b3 = points2 + (bi * m + i3) * c2;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                int col = col0 + t;
+                if (col < c2) {
+                    // (p1*w1+p2*w2)+p3*w3, no FMA: tf_interpolate.cpp:107-127
+                    v[t] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(b1 + col), w1), __fmul_rn(__ldg(b2 + col), w2)), __fmul_rn(__ldg(b3 + col), w3));
+                } else {
+                    int q = col - c2;
+                    v[t] = q < c1 ? __ldg(points1 + row * c1 + q) : 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                int q = col0 + t - c2;
+                v[t] = q < c1 ? __ldg(points1 + row * c1 + q) : 0.f;
+            }
+        }
+        uint4 pk = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        *reinterpret_cast<uint4 *>(img + tile_chunk_offset(row, ch, ld)) = pk;
+    }
+}
+
+}  // namespace gspn
+
+using namespace gspn;
+
+extern "C" size_t gspn_mlp_weight_image_bytes(int cin_padded, int cout) {
+    if (cin_padded <= 0 || cout <= 0 || cin_padded % 64 || cout % 8) return 0;
+    return (size_t)(cin_padded / 64) * (size_t)cout * 128;
+}
+
+extern "C" int gspn_mlp_pack_weights(int cin, int cin_padded, int cout, const float *w_f32, const int *row_perm, void *wimg,
+                                     gspn_stream_t stream) {
+    GSPN_REQUIRE(cin > 0 && cin_padded >= cin && cin_padded % 64 == 0 && cout > 0 && cout % 8 == 0);
+    GSPN_REQUIRE_PTR(w_f32); GSPN_REQUIRE_PTR(wimg);
+    long total = (long)cin_padded * cout;
+    pack_weights_kernel<<<(unsigned)ceil_div_l(total, 256), 256, 0, as_stream(stream)>>>(cin, cin_padded, cout, w_f32, row_perm,
+                                                                                        (unsigned char *)wimg);
+    return check_launch();
+}
+
+extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a, const void *const *wimg, const float *const *scale,
+                              const float *const *shift, const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream) {
+    GSPN_REQUIRE(rows >= 0 && nlayers >= 1 && nlayers <= kMaxLayers && pool >= 1);
+    GSPN_REQUIRE_PTR(dims); GSPN_REQUIRE_PTR(wimg); GSPN_REQUIRE_PTR(scale); GSPN_REQUIRE_PTR(shift); GSPN_REQUIRE_PTR(relu);
+    if (rows == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(a);
+    if (out_f32 == nullptr && out_bf16 == nullptr) return GSPN_E_NULL_PTR;
+    ChainParams p = {};
+    p.rows = rows;
+    p.ntiles = ceil_div_l(rows, kTileRows);
+    p.nlayers = nlayers;
+    int maxn = 0;
+    size_t affine_floats = 0;
+    for (int l = 0; l < nlayers; ++l) {
+        p.K[l] = l == 0 ? dims[0] : ((dims[l] + 63) / 64) * 64;
+        p.N[l] = dims[l + 1];
+        GSPN_REQUIRE(p.K[l] > 0 && p.K[l] % 64 == 0 && p.N[l] > 0);
+        if (p.N[l] % 32 != 0 || p.N[l] > 512) return GSPN_E_UNSUPPORTED;  // use the fp32 path
+        GSPN_REQUIRE_PTR(wimg[l]); GSPN_REQUIRE_PTR(scale[l]); GSPN_REQUIRE_PTR(shift[l]);
+        p.wimg[l] = (const unsigned char *)wimg[l];
+        p.scale[l] = scale[l];
+        p.shift[l] = shift[l];
+        p.relu[l] = relu[l];
+        maxn = p.N[l] > maxn ? p.N[l] : maxn;
+        affine_floats += 2 * (size_t)p.N[l];
+    }
+    if (pool > 1) {
+        if (pool % 32 != 0 || rows % pool != 0 || !relu[nlayers - 1]) return GSPN_E_UNSUPPORTED;
+        if (pool != 32 && (out_f32 == nullptr || out_bf16 != nullptr)) return GSPN_E_UNSUPPORTED;
+    }
+    p.a = (const unsigned char *)a;
+    p.pool = pool;
+    p.out_f32 = out_f32;
+    p.out_bf16 = (__nv_bfloat16 *)out_bf16;
+    p.nch = maxn < 128 ? maxn : 128;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < maxn) p.tmem_cols <<= 1;
+    // region 0 holds the layer-0 input tile and the outputs of odd layers; region 1 the outputs of even layers
+    int r0k = p.K[0], r1k = 64;
+    for (int l = 0; l + 1 < nlayers; ++l) {
+        int kp = ((p.N[l] + 63) / 64) * 64;
+        if (l & 1) r0k = kp > r0k ? kp : r0k; else r1k = kp > r1k ? kp : r1k;
+    }
+    p.r0_bytes = (uint32_t)(r0k / 64) * kTileBytes;
+    p.r1_bytes = (uint32_t)(r1k / 64) * kTileBytes;
+    p.stage_bytes = (uint32_t)p.nch * 128u;
+    size_t smem = 1024 + (size_t)p.r0_bytes + p.r1_bytes + (size_t)kStages * p.stage_bytes + affine_floats * sizeof(float);
+    if (smem > 227 * 1024) return GSPN_E_UNSUPPORTED;
+    // TMEM holds 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by inflating the smem request
+    int occ_tmem = 512 / p.tmem_cols;
+    size_t min_smem = (size_t)(228 * 1024) / (occ_tmem + 1) + 1;
+    if (smem < min_smem) smem = min_smem;
+    cudaStream_t s = as_stream(stream);
+    GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    GSPN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlp_chain_kernel, kTcThreads, smem));
+    if (occ < 1) return GSPN_E_UNSUPPORTED;
+    if (occ > occ_tmem) occ = occ_tmem;
+    int dev = 0, sms = 148;
+    GSPN_CUDA_OK(cudaGetDevice(&dev));
+    GSPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long grid = (long)sms * occ;
+    if (grid > p.ntiles) grid = p.ntiles;
+    if (pool > 1 && pool != 32)
+        GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
+    mlp_chain_kernel<<<(unsigned)grid, kTcThreads, smem, s>>>(p);
+    return check_launch();
+}
+
+extern "C" int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float *points1, const float *points2, const int *idx,
+                                const float *weight, void *a_img, int ld, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m > 0 && c1 >= 0 && c2 > 0 && ld % 64 == 0 && ld >= c1 + c2);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(points2); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(weight); GSPN_REQUIRE_PTR(a_img);
+    if (c1 > 0) GSPN_REQUIRE_PTR(points1);
+    long rows = (long)b * n;
+    long total = rows * (ld / 8);
+    long blk = ceil_div_l(total, 256);
+    if (blk > 148L * 64) blk = 148L * 64;
+    fp_assemble_kernel<<<(unsigned)blk, 256, 0, as_stream(stream)>>>(rows, n, m, c1, c2, points1, points2, idx, weight, (unsigned char *)a_img, ld);
+    return check_launch();
+}

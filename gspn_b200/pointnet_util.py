@@ -67,14 +67,22 @@ VARIABLES = VariableStore()
 
 
 def fold_layer(layer):
-    """conv bias + inference batch norm as one affine: y = (x@W)*scale + shift."""
+    """conv bias + inference batch norm as one affine: y = (x@W)*scale + shift.  Cached on the layer
+    dict (re-folded when any of the tensors is replaced or modified in place)."""
+    names = ("biases", "gamma", "beta", "moving_mean", "moving_variance")
+    sig = tuple((layer[k].data_ptr(), layer[k]._version) for k in names if layer.get(k) is not None)
+    cached = layer.get("_folded")
+    if cached is not None and cached[0] == sig:
+        return cached[1], cached[2]
     if layer.get("gamma") is not None:
         scale = layer["gamma"] / torch.sqrt(layer["moving_variance"] + BN_EPS)
         shift = (layer["biases"] - layer["moving_mean"]) * scale + layer["beta"]
     else:
         scale = torch.ones_like(layer["biases"])
         shift = layer["biases"]
-    return scale.contiguous(), shift.contiguous()
+    scale, shift = scale.contiguous(), shift.contiguous()
+    layer["_folded"] = (sig, scale, shift)
+    return scale, shift
 
 
 class _Null:
@@ -140,14 +148,23 @@ def _run_mlp_f32(x2d, layers, pool_last=1):
     return x2d
 
 
-def _features_first(w, c, use_xyz, has_points):
-    """Rows of the first-layer kernel re-ordered for the fused grouping layout [features | xyz].
-    Reference order is [xyz | features] (pointnet_util.py:48)."""
+def _features_first(layer, c, use_xyz, has_points):
+    """First-layer dict whose kernel rows are re-ordered for the fused grouping layout [features | xyz]
+    (reference order is [xyz | features], pointnet_util.py:48).  Cached on the layer dict."""
+    w = layer["weights"]
     if not has_points:
-        return w  # rows are xyz only
-    if use_xyz:
-        return torch.cat([w[3:], w[:3]], dim=0).contiguous()
-    return torch.cat([w, torch.zeros((3, w.shape[1]), dtype=w.dtype, device=w.device)], dim=0)  # xyz columns ignored
+        return layer  # rows are xyz only
+    sig = (w.data_ptr(), w._version, use_xyz)
+    cached = layer.get("_ff")
+    if cached is None or cached[0] != sig:
+        if use_xyz:
+            wp = torch.cat([w[3:], w[:3]], dim=0).contiguous()
+        else:
+            wp = torch.cat([w, torch.zeros((3, w.shape[1]), dtype=w.dtype, device=w.device)], dim=0)  # xyz columns ignored
+        layer["_ff"] = cached = (sig, wp)
+    first = dict(layer)
+    first["weights"] = cached[1]
+    return first
 
 
 def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_all, is_training, bn_decay, scope, bn=True,
@@ -181,8 +198,7 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
                 idx, _, grouped, _ = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
             with _stage(timers, scope + ":mlp"):
                 if layers:
-                    first = dict(layers[0])
-                    first["weights"] = _features_first(first["weights"], c, use_xyz, points is not None)
+                    first = _features_first(layers[0], c, use_xyz, points is not None)
                     x = _run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
                 else:
                     x = ops.mlp_pool(grouped, nsample)
