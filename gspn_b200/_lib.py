@@ -28,6 +28,7 @@ SIGNATURES = {
     "gspn_fps_max_resident_points": (c_int, []),
     "gspn_farthest_point_sample": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "gspn_farthest_point_sample_cfg": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P]),
+    "gspn_fps_profile": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P]),
     "gspn_gather_point": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_gather_point_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, P, P, P, P, P]),

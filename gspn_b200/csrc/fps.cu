@@ -113,9 +113,11 @@ struct Tourney {
 // Requires (blockDim.x*CLUSTER) % 512 == 0 or PPT == 1 so that a thread's points have ascending keys,
 // and CLUSTER * (blockDim.x/32) <= kMaxCand when CLUSTER > 1.
 // dynamic smem: float4 xyz copy, [PPT][blockDim.x], so only the round's winner lane fetches coordinates.
-template <int PPT, int CLUSTER, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out) {
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false>
+__global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out,
+                                                               long long *__restrict__ prof = nullptr) {
     extern __shared__ float4 sxyz[];
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc[4] = {0, 0, 0, 0};
     __shared__ Slot wslot[2][CLUSTER > 1 ? kMaxCand : kMaxWarps];
     __shared__ unsigned wkey[2][CLUSTER > 1 ? kMaxCand : kMaxWarps];
     __shared__ __align__(8) uint64_t xbar[2];
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         const int par = r & 1;
         if (CLUSTER > 1 && threadIdx.x == 0)  // this round's phase completes after ncand x (16+4) bytes have landed
             f_mbar_expect_tx(f_smem_u32(&xbar[par]), (uint32_t)ncand * 20u);
+        if (PROFILE) t0 = clock64();
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             float d = sqdist_fma(px[j], py[j], pz[j], x1, y1, z1);
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         float best;
         int bj;
         Tourney<0, PPT>::run(td, best, bj);
+        if (PROFILE) { asm volatile("" ::"f"(best), "r"(bj)); t1 = clock64(); }
         Cand c;
         c.dbits = __float_as_int(best);
         c.key = fps_key(gtid + bj * T);
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         int wm = __reduce_max_sync(GSPN_FULL_MASK, c.dbits);
         unsigned kk = (c.dbits == wm) ? c.key : 0xFFFFFFFFu;
         unsigned wk = __reduce_min_sync(GSPN_FULL_MASK, kk);
+        if (PROFILE) { asm volatile("" ::"r"(wk)); t2 = clock64(); }
         if (CLUSTER == 1) {
             if (kk == wk) {
                 float4 q = sxyz[bj * blockDim.x + threadIdx.x];
@@ -196,6 +201,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
             }
             f_mbar_wait(f_smem_u32(&xbar[par]), (uint32_t)(((r - 1) >> 1) & 1));  // barrier par serves rounds par, par+2, ...
         }
+        if (PROFILE) t3 = clock64();
         // every warp reduces the candidate table (<= kMaxCand entries, strided over the lanes)
         const int cnt = CLUSTER == 1 ? nwarps : ncand;
         Cand w;
@@ -208,6 +214,14 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         c = warp_argmax(w);
         x1 = c.x; y1 = c.y; z1 = c.z;
         if (gtid == 0) out[(size_t)cloud * m + r] = fps_unkey(c.key);
+        if (PROFILE) {
+            asm volatile("" ::"f"(x1));
+            long long t4 = clock64();
+            acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2; acc[3] += t4 - t3;
+        }
+    }
+    if (PROFILE && gtid == 0 && cloud == 0 && prof) {
+        prof[0] = acc[0]; prof[1] = acc[1]; prof[2] = acc[2]; prof[3] = acc[3];
     }
     if (CLUSTER > 1) cluster_barrier();  // no CTA exits while a peer may still address its smem
 }
@@ -260,9 +274,9 @@ __global__ void __launch_bounds__(1024, 1) fps_stream_kernel(int n, int m, const
     }
 }
 
-template <int PPT, int CLUSTER, int MAXT>
-static int launch_resident(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s) {
-    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT>;
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false>
+static int launch_resident(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s, long long *prof = nullptr) {
+    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT, PROFILE>;
     if (CLUSTER > 8) GSPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER, b, 1);
@@ -278,7 +292,7 @@ static int launch_resident(int b, int n, int m, const float *inp, int *out, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out));
+    GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out, prof));
     return GSPN_OK;
 }
 
@@ -330,6 +344,24 @@ constexpr int kMaxResident = 512 * 16 * 16;
 }  // namespace gspn
 
 using namespace gspn;
+
+// Tuning door: per-phase cycle counts of thread 0 (compute+tournament, warp reduce, exchange, table reduce),
+// summed over the m-1 rounds, for the (threads, ppt, cluster) shapes the default table uses.
+extern "C" int gspn_fps_profile(int b, int n, int m, const float *inp, int *out, int threads, int ppt, int cluster, long long *prof4,
+                                gspn_stream_t stream) {
+    GSPN_REQUIRE(b > 0 && n > 0 && m > 0);
+    GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out); GSPN_REQUIRE_PTR(prof4);
+    if ((long)threads * ppt * cluster < n || (cluster > 1 && cluster * (threads / 32) > kMaxCand)) return GSPN_E_UNSUPPORTED;
+    cudaStream_t s = as_stream(stream);
+    int rc = GSPN_E_UNSUPPORTED;
+    if (ppt == 32 && cluster == 8 && threads <= 256) rc = launch_resident<32, 8, 256, true>(b, n, m, inp, out, threads, s, prof4);
+    else if (ppt == 16 && cluster == 8 && threads <= 512) rc = launch_resident<16, 8, 512, true>(b, n, m, inp, out, threads, s, prof4);
+    else if (ppt == 4 && cluster == 1) rc = launch_resident<4, 1, 1024, true>(b, n, m, inp, out, threads, s, prof4);
+    else if (ppt == 4 && cluster == 8) rc = launch_resident<4, 8, 1024, true>(b, n, m, inp, out, threads, s, prof4);
+    else if (ppt == 4 && cluster == 16) rc = launch_resident<4, 16, 1024, true>(b, n, m, inp, out, threads, s, prof4);
+    if (rc != GSPN_OK) return rc;
+    return check_launch();
+}
 
 extern "C" int gspn_fps_max_resident_points(void) { return kMaxResident; }
 

@@ -22,7 +22,7 @@ namespace gspn {
 
 constexpr int kMaxLayers = 4;
 constexpr int kTcThreads = 128;
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 
 struct ChainParams {
     long rows;
@@ -40,6 +40,7 @@ struct ChainParams {
     __nv_bfloat16 *out_bf16;
     int nch;  // weight rows (output channels) per ring stage / per MMA
     int tmem_cols;
+    int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
     uint32_t r0_bytes, r1_bytes, stage_bytes;
 };
 
@@ -107,13 +108,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-struct Cursor {  // position in the per-tile weight block sequence: layer, n-chunk, k-block
-    int l, nc, kb;
+struct Cursor {  // position in the per-tile weight block sequence: layer, k-block, n-chunk (fastest)
+    int l, kb, nc;
     __device__ __forceinline__ void advance(const ChainParams &p) {
-        if (++kb == (p.K[l] >> 6)) {
-            kb = 0;
-            if (++nc == (p.N[l] + p.nch - 1) / p.nch) {
-                nc = 0;
+        if (++nc == (p.N[l] + p.nch - 1) / p.nch) {
+            nc = 0;
+            if (++kb == (p.K[l] >> 6)) {
+                kb = 0;
                 if (++l == p.nlayers) l = 0;
             }
         }
@@ -123,21 +124,24 @@ struct Cursor {  // position in the per-tile weight block sequence: layer, n-chu
 __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 2];
+    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = s_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
     unsigned char *sm = smem_raw + (base - raw);
+    // layer l>0 reads R[(l-1)&1]; layer l (not last) writes R[l&1]
     const uint32_t R[2] = {base, base + p.r0_bytes};
     unsigned char *Rg[2] = {sm, sm + p.r0_bytes};
-    const uint32_t stg = base + p.r0_bytes + p.r1_bytes;
-    float *affine = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)kStages * p.stage_bytes);
-    const uint32_t full0 = s_u32(&bars[0]), empty0 = s_u32(&bars[kStages]), a_full = s_u32(&bars[2 * kStages]),
-                   mma_done = s_u32(&bars[2 * kStages + 1]);
+    const uint32_t aring = base + p.r0_bytes + p.r1_bytes;
+    const uint32_t wring = aring + (uint32_t)p.a_stages * kTileBytes;
+    float *affine = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes +
+                                              (size_t)p.w_stages * p.stage_bytes);
+    const uint32_t w_full = s_u32(&bars[0]), w_empty = s_u32(&bars[kMaxStages]), a_full = s_u32(&bars[2 * kMaxStages]),
+                   a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]);
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * kStages + 2; ++i) mb_init(s_u32(&bars[i]), 1);
+        for (int i = 0; i < 4 * kMaxStages + 1; ++i) mb_init(s_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
@@ -171,50 +175,74 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
 
     int blocks_per_tile = 0;
     for (int l = 0; l < p.nlayers; ++l) blocks_per_tile += ((p.N[l] + p.nch - 1) / p.nch) * (p.K[l] >> 6);
-    long my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const long total_blocks = my_tiles * blocks_per_tile;
-    long issued = 0, used = 0;  // weight blocks requested / consumed (thread 0 only)
-    Cursor ic = {0, 0, 0};
-    uint32_t a_par = 0, done_par = 0;
     const int kb0 = p.K[0] >> 6;
+    const long my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long total_w = my_tiles * blocks_per_tile, total_a = my_tiles * kb0;
+    long w_issued = 0, w_used = 0, a_issued = 0, a_used = 0;  // ring positions (thread 0 only)
+    Cursor wc = {0, 0, 0};
+    uint32_t done_par = 0;
+
+    // thread 0: keep both rings full; they run ahead across layers and tiles (next tile's input prefetches
+    // while this tile's later layers compute)
+    auto top_up = [&]() {
+        while (a_issued < total_a && a_issued < a_used + p.a_stages) {
+            const int s = (int)(a_issued % p.a_stages);
+            const long round = a_issued / p.a_stages;
+            if (round > 0) mb_wait(a_empty + 8 * s, (uint32_t)((round - 1) & 1));
+            const long t = blockIdx.x + (a_issued / kb0) * gridDim.x;
+            const int kb = (int)(a_issued % kb0);
+            mb_expect_tx(a_full + 8 * s, kTileBytes);
+            bulk_load(aring + s * kTileBytes, p.a + ((size_t)t * kb0 + kb) * kTileBytes, kTileBytes, a_full + 8 * s);
+            ++a_issued;
+        }
+        while (w_issued < total_w && w_issued < w_used + p.w_stages) {
+            const int s = (int)(w_issued % p.w_stages);
+            const long round = w_issued / p.w_stages;
+            if (round > 0) mb_wait(w_empty + 8 * s, (uint32_t)((round - 1) & 1));
+            const int rows_i = min(p.nch, p.N[wc.l] - wc.nc * p.nch);
+            const uint32_t bytes = (uint32_t)rows_i * 128u;
+            mb_expect_tx(w_full + 8 * s, bytes);
+            bulk_load(wring + s * p.stage_bytes, p.wimg[wc.l] + (size_t)wc.kb * p.N[wc.l] * 128 + (size_t)wc.nc * p.nch * 128, bytes,
+                      w_full + 8 * s);
+            wc.advance(p);
+            ++w_issued;
+        }
+    };
 
     for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        if (tid == 0) {
-            mb_expect_tx(a_full, (uint32_t)kb0 * kTileBytes);
-            for (int kb = 0; kb < kb0; ++kb) bulk_load(R[0] + kb * kTileBytes, p.a + ((size_t)tile * kb0 + kb) * kTileBytes, kTileBytes, a_full);
-        }
         for (int l = 0; l < p.nlayers; ++l) {
-            const uint32_t in = R[l & 1];
             const int Nl = p.N[l], KBl = p.K[l] >> 6;
             if (tid == 0) {
-                if (l == 0) { mb_wait(a_full, a_par); }
                 tc_fence_after();
                 const int nchunks = (Nl + p.nch - 1) / p.nch;
-                for (int nc = 0; nc < nchunks; ++nc) {
-                    const int nrows = min(p.nch, Nl - nc * p.nch);
-                    const uint32_t idesc = instr_desc(128, nrows);
-                    for (int kb = 0; kb < KBl; ++kb) {
-                        while (issued < total_blocks && issued < used + kStages) {  // keep the ring full
-                            const int s = (int)(issued % kStages);
-                            const long round = issued / kStages;
-                            if (round > 0) mb_wait(empty0 + 8 * s, (uint32_t)((round - 1) & 1));
-                            const int rows_i = min(p.nch, p.N[ic.l] - ic.nc * p.nch);
-                            const uint32_t bytes = (uint32_t)rows_i * 128u;
-                            mb_expect_tx(full0 + 8 * s, bytes);
-                            bulk_load(stg + s * p.stage_bytes,
-                                      p.wimg[ic.l] + (size_t)ic.kb * p.N[ic.l] * 128 + (size_t)ic.nc * p.nch * 128, bytes, full0 + 8 * s);
-                            ic.advance(p);
-                            ++issued;
-                        }
-                        const int s = (int)(used % kStages);
-                        mb_wait(full0 + 8 * s, (uint32_t)((used / kStages) & 1));
+                for (int kb = 0; kb < KBl; ++kb) {
+                    uint32_t a_addr;
+                    if (l == 0) {
+                        top_up();
+                        const int sa = (int)(a_used % p.a_stages);
+                        mb_wait(a_full + 8 * sa, (uint32_t)((a_used / p.a_stages) & 1));
+                        a_addr = aring + sa * kTileBytes;
+                    } else {
+                        a_addr = R[(l - 1) & 1] + kb * kTileBytes;
+                    }
+                    const uint64_t ad = smem_desc(a_addr);
+                    for (int nc = 0; nc < nchunks; ++nc) {
+                        top_up();
+                        const int s = (int)(w_used % p.w_stages);
+                        mb_wait(w_full + 8 * s, (uint32_t)((w_used / p.w_stages) & 1));
                         tc_fence_after();
-                        const uint64_t ad = smem_desc(in + kb * kTileBytes), bd = smem_desc(stg + s * p.stage_bytes);
+                        const int nrows = min(p.nch, Nl - nc * p.nch);
+                        const uint32_t idesc = instr_desc(128, nrows);
+                        const uint64_t bd = smem_desc(wring + s * p.stage_bytes);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
                             tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-                        tc_commit(empty0 + 8 * s);  // stage free when these MMAs have read it
-                        ++used;
+                        tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
+                        ++w_used;
+                    }
+                    if (l == 0) {
+                        tc_commit(a_empty + 8 * (int)(a_used % p.a_stages));
+                        ++a_used;
                     }
                 }
                 tc_commit(mma_done);
@@ -229,7 +257,7 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
             const float *sc = affine + aoff[l], *sh = sc + Nl;
             const int row = warp * 32 + lane;
             const long grow = tile * kTileRows + row;
-            unsigned char *outb = Rg[(l + 1) & 1];
+            unsigned char *outb = Rg[l & 1];
             for (int c0 = 0; c0 < Nl; c0 += 32) {
                 uint32_t v[32];
                 tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
@@ -288,7 +316,6 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
             fence_proxy_async();  // epilogue st.shared -> visible to the tensor core's async-proxy reads
             __syncthreads();
         }
-        a_par ^= 1;
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
@@ -405,17 +432,26 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     p.nch = maxn < 128 ? maxn : 128;
     p.tmem_cols = 32;
     while (p.tmem_cols < maxn) p.tmem_cols <<= 1;
-    // region 0 holds the layer-0 input tile and the outputs of odd layers; region 1 the outputs of even layers
-    int r0k = p.K[0], r1k = 64;
+    // region l&1 holds the output of (non-last) layer l, i.e. the next layer's A operand
+    int rk[2] = {0, 0};
     for (int l = 0; l + 1 < nlayers; ++l) {
         int kp = ((p.N[l] + 63) / 64) * 64;
-        if (l & 1) r0k = kp > r0k ? kp : r0k; else r1k = kp > r1k ? kp : r1k;
+        rk[l & 1] = kp > rk[l & 1] ? kp : rk[l & 1];
     }
-    p.r0_bytes = (uint32_t)(r0k / 64) * kTileBytes;
-    p.r1_bytes = (uint32_t)(r1k / 64) * kTileBytes;
+    p.r0_bytes = (uint32_t)(rk[0] / 64) * kTileBytes;
+    p.r1_bytes = (uint32_t)(rk[1] / 64) * kTileBytes;
     p.stage_bytes = (uint32_t)p.nch * 128u;
-    size_t smem = 1024 + (size_t)p.r0_bytes + p.r1_bytes + (size_t)kStages * p.stage_bytes + affine_floats * sizeof(float);
-    if (smem > 227 * 1024) return GSPN_E_UNSUPPORTED;
+    size_t smem = 0;
+    const int tries[4][2] = {{3, 4}, {2, 4}, {2, 3}, {2, 2}};
+    bool fits = false;
+    for (int t = 0; t < 4 && !fits; ++t) {
+        p.a_stages = tries[t][0];
+        p.w_stages = tries[t][1];
+        smem = 1024 + (size_t)p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes + (size_t)p.w_stages * p.stage_bytes +
+               affine_floats * sizeof(float);
+        fits = smem <= 227 * 1024;
+    }
+    if (!fits) return GSPN_E_UNSUPPORTED;
     // TMEM holds 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by inflating the smem request
     int occ_tmem = 512 / p.tmem_cols;
     size_t min_smem = (size_t)(228 * 1024) / (occ_tmem + 1) + 1;

@@ -68,6 +68,11 @@ int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out,
 int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *out,
                                    int threads, int ppt, int cluster, gspn_stream_t stream);
 
+/* Tuning door: per-phase SM-cycle counts of thread 0 of cloud 0, summed over the m-1 rounds:
+ * prof4[0..3] = distance update + argmax, warp reduce, candidate exchange, table reduce. */
+int gspn_fps_profile(int b, int n, int m, const float *inp, int *out, int threads, int ppt, int cluster,
+                     long long *prof4, gspn_stream_t stream);
+
 /* gather_point(inp, idx)  tf_sampling.py:29-37; gatherpointLauncher tf_sampling_g.cu:206
  * inp (b,n,c) , idx (b,m) -> out (b,m,c).  The reference is hard-wired to c=3;
  * c is explicit here because the model also gathers colour (model_rpointnet.py:151). */
