@@ -284,9 +284,10 @@ using namespace gspn;
 static int launch_ballquery(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
                             GroupArgs g, cudaStream_t s) {
     const float s_max = ball_threshold(radius);
-    // QPW: more queries per warp amortise the shared-memory reads, but need enough warps to fill 148 SMs
+    // QPW: more queries per warp amortise the shared-memory reads and give independent FMA chains,
+    // as long as one 8-warp CTA per SM remains
     long warps1 = (long)b * m;
-    int qpw = warps1 >= 148L * 8 * 8 * 4 ? 4 : (warps1 >= 148L * 8 * 8 * 2 ? 2 : 1);
+    int qpw = warps1 >= 148L * 8 * 4 ? 4 : (warps1 >= 148L * 8 * 2 ? 2 : 1);
     if ((size_t)qpw * nsample * 4 * kBQWarps > 96 * 1024) qpw = 1;
     size_t smem = (size_t)2 * kBQTile * 3 * 4 + (size_t)kBQWarps * qpw * nsample * 4;
     if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;

@@ -113,13 +113,15 @@ struct Tourney {
 // Requires (blockDim.x*CLUSTER) % 512 == 0 or PPT == 1 so that a thread's points have ascending keys,
 // and CLUSTER * (blockDim.x/32) <= kMaxCand when CLUSTER > 1.
 // dynamic smem: float4 xyz copy, [PPT][blockDim.x], so only the round's winner lane fetches coordinates.
-template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false>
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false, int CPL = (CLUSTER > 1 ? 2 : 1)>
 __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out,
                                                                long long *__restrict__ prof = nullptr) {
     extern __shared__ float4 sxyz[];
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc[4] = {0, 0, 0, 0};
-    __shared__ Slot wslot[2][CLUSTER > 1 ? kMaxCand : kMaxWarps];
-    __shared__ unsigned wkey[2][CLUSTER > 1 ? kMaxCand : kMaxWarps];
+    // candidate table: 32*CPL entries per parity; entries no warp owns stay "empty" (-1, max key) forever,
+    // so the per-round reduce is CPL unconditional loads per lane
+    __shared__ Slot wslot[2][32 * CPL];
+    __shared__ unsigned wkey[2][32 * CPL];
     __shared__ __align__(8) uint64_t xbar[2];
 
     const int cloud = blockIdx.y;
@@ -146,6 +148,11 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
     float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
     if (gtid == 0) out[(size_t)cloud * m] = 0;
     const int ncand = CLUSTER * nwarps;
+    for (int i = threadIdx.x; i < 2 * 32 * CPL; i += blockDim.x) {
+        (&wslot[0][0])[i] = Slot{0.f, 0.f, 0.f, __float_as_int(-1.0f)};
+        (&wkey[0][0])[i] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
     if (CLUSTER > 1) {
         if (threadIdx.x == 0) {
             f_mbar_init(f_smem_u32(&xbar[0]), 1);
@@ -172,14 +179,14 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         Cand c;
         c.dbits = __float_as_int(best);
         c.key = fps_key(gtid + bj * T);
-        // warp-level winner; its lane alone fetches the coordinates from the smem copy
+        // every lane starts fetching its own best point's coordinates; the load overlaps the warp reduce
+        const float4 q = sxyz[bj * blockDim.x + threadIdx.x];
         int wm = __reduce_max_sync(GSPN_FULL_MASK, c.dbits);
         unsigned kk = (c.dbits == wm) ? c.key : 0xFFFFFFFFu;
         unsigned wk = __reduce_min_sync(GSPN_FULL_MASK, kk);
         if (PROFILE) { asm volatile("" ::"r"(wk)); t2 = clock64(); }
         if (CLUSTER == 1) {
             if (kk == wk) {
-                float4 q = sxyz[bj * blockDim.x + threadIdx.x];
                 wslot[par][warp] = Slot{q.x, q.y, q.z, wm};
                 wkey[par][warp] = wk;
             }
@@ -187,29 +194,32 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         } else {
             // all-to-all: the winner's (x,y,z,d | key) goes straight into every CTA's table
             const int src = __ffs(__ballot_sync(GSPN_FULL_MASK, kk == wk)) - 1;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane == src) q = sxyz[bj * blockDim.x + threadIdx.x];
-            q.x = __shfl_sync(GSPN_FULL_MASK, q.x, src);
-            q.y = __shfl_sync(GSPN_FULL_MASK, q.y, src);
-            q.z = __shfl_sync(GSPN_FULL_MASK, q.z, src);
+            const float qx = __shfl_sync(GSPN_FULL_MASK, q.x, src);
+            const float qy = __shfl_sync(GSPN_FULL_MASK, q.y, src);
+            const float qz = __shfl_sync(GSPN_FULL_MASK, q.z, src);
             if (lane < CLUSTER) {
                 const int slot = rank * nwarps + warp;
                 const uint32_t rbar = map_to_rank(f_smem_u32(&xbar[par]), lane);
-                st_async_v4(map_to_rank(f_smem_u32(&wslot[par][slot]), lane), __float_as_uint(q.x), __float_as_uint(q.y),
-                            __float_as_uint(q.z), (uint32_t)wm, rbar);
+                st_async_v4(map_to_rank(f_smem_u32(&wslot[par][slot]), lane), __float_as_uint(qx), __float_as_uint(qy),
+                            __float_as_uint(qz), (uint32_t)wm, rbar);
                 st_async_b32(map_to_rank(f_smem_u32(&wkey[par][slot]), lane), wk, rbar);
             }
             f_mbar_wait(f_smem_u32(&xbar[par]), (uint32_t)(((r - 1) >> 1) & 1));  // barrier par serves rounds par, par+2, ...
         }
         if (PROFILE) t3 = clock64();
-        // every warp reduces the candidate table (<= kMaxCand entries, strided over the lanes)
-        const int cnt = CLUSTER == 1 ? nwarps : ncand;
+        // every warp reduces the candidate table: CPL unconditional loads per lane, then one warp argmax
         Cand w;
-        w.dbits = __float_as_int(-1.0f); w.key = 0xFFFFFFFFu; w.x = w.y = w.z = 0.f;
-        for (int i = lane; i < cnt; i += 32) {
-            Slot s = wslot[par][i];
-            unsigned k2 = wkey[par][i];
-            if (s.dbits > w.dbits || (s.dbits == w.dbits && k2 < w.key)) { w.dbits = s.dbits; w.key = k2; w.x = s.x; w.y = s.y; w.z = s.z; }
+        {
+            Slot s0 = wslot[par][lane];
+            w.dbits = s0.dbits; w.key = wkey[par][lane]; w.x = s0.x; w.y = s0.y; w.z = s0.z;
+        }
+#pragma unroll
+        for (int i = 1; i < CPL; ++i) {
+            Slot s = wslot[par][lane + 32 * i];
+            unsigned k2 = wkey[par][lane + 32 * i];
+            bool take = s.dbits > w.dbits || (s.dbits == w.dbits && k2 < w.key);
+            w.dbits = take ? s.dbits : w.dbits; w.key = take ? k2 : w.key;
+            w.x = take ? s.x : w.x; w.y = take ? s.y : w.y; w.z = take ? s.z : w.z;
         }
         c = warp_argmax(w);
         x1 = c.x; y1 = c.y; z1 = c.z;
@@ -274,9 +284,9 @@ __global__ void __launch_bounds__(1024, 1) fps_stream_kernel(int n, int m, const
     }
 }
 
-template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false>
-static int launch_resident(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s, long long *prof = nullptr) {
-    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT, PROFILE>;
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE, int CPL>
+static int launch_resident_cpl(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s, long long *prof) {
+    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT, PROFILE, CPL>;
     if (CLUSTER > 8) GSPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CLUSTER, b, 1);
@@ -294,6 +304,15 @@ static int launch_resident(int b, int n, int m, const float *inp, int *out, int 
     cfg.numAttrs = 1;
     GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out, prof));
     return GSPN_OK;
+}
+
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false>
+static int launch_resident(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s, long long *prof = nullptr) {
+    const int ncand = CLUSTER * (threads / 32);
+    if (CLUSTER == 1 || ncand <= 32) return launch_resident_cpl<PPT, CLUSTER, MAXT, PROFILE, 1>(b, n, m, inp, out, threads, s, prof);
+    if (ncand <= 64) return launch_resident_cpl<PPT, CLUSTER, MAXT, PROFILE, 2>(b, n, m, inp, out, threads, s, prof);
+    if (!PROFILE && ncand <= 128) return launch_resident_cpl<PPT, CLUSTER, MAXT, false, 4>(b, n, m, inp, out, threads, s, prof);
+    return GSPN_E_UNSUPPORTED;
 }
 
 template <int PPT, int MAXT>
@@ -331,10 +350,12 @@ static void choose_cfg(int n, int *threads, int *ppt, int *cluster) {
     if (n <= 512) { *threads = ((n + 31) / 32) * 32; *ppt = 1; *cluster = 1; return; }
     if (n <= 1024) { *threads = 512; *ppt = 2; *cluster = 1; return; }
     if (n <= 2048) { *threads = 512; *ppt = 4; *cluster = 1; return; }
-    if (n <= 4096) { *threads = 512; *ppt = 8; *cluster = 1; return; }
-    if (n <= 8192) { *threads = 256; *ppt = 16; *cluster = 2; return; }
-    if (n <= 16384) { *threads = 256; *ppt = 16; *cluster = 4; return; }
-    if (n <= 32768) { *threads = 256; *ppt = 16; *cluster = 8; return; }
+    // measured on B200 (tools/fps_sweep.py, profiles/r01_fps_sweep.txt): few fat warps win -- one warp per SM
+    // sub-partition keeps the candidate exchange small, registers hold 32 points per thread
+    if (n <= 4096) { *threads = 128; *ppt = 8; *cluster = 4; return; }
+    if (n <= 8192) { *threads = 128; *ppt = 16; *cluster = 4; return; }
+    if (n <= 16384) { *threads = 128; *ppt = 16; *cluster = 8; return; }
+    if (n <= 32768) { *threads = 128; *ppt = 32; *cluster = 8; return; }
     if (n <= 65536) { *threads = 256; *ppt = 32; *cluster = 8; return; }
     *threads = 256; *ppt = 32; *cluster = 16;  // up to 131072 (non-portable cluster size)
 }
