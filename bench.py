@@ -302,6 +302,9 @@ def main():
     torch.cuda.synchronize(); barrier()
     e2e_ms = e_start.elapsed_time(e_end) / args.steps
     # ---- per-stage breakdown: the same K steps, eager and in order on one stream, bracketed by CUDA events
+    for s in range(2):  # eager warm-up (allocator pools of the default stream)
+        backbone.forward(*dev_in[s % ROTATE], store, precision=precision)
+    torch.cuda.synchronize()
     timers.on = True
     calls0 = _lib.CALLS[0]
     for s in range(args.steps):

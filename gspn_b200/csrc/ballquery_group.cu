@@ -19,6 +19,7 @@
 //     in the layout its only consumer wants.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gspn {
@@ -287,7 +288,11 @@ static int launch_ballquery(int b, int n, int m, float radius, int nsample, cons
     // QPW: more queries per warp amortise the shared-memory reads and give independent FMA chains,
     // as long as one 8-warp CTA per SM remains
     long warps1 = (long)b * m;
-    int qpw = warps1 >= 148L * 8 * 4 ? 4 : (warps1 >= 148L * 8 * 2 ? 2 : 1);
+    int qpw = warps1 >= 148L * 8 * 4 ? 2 : 1;  // measured (tools/op_bench.py): 2 beats 1 and 4 on 8 x 32768 -> 2048
+    if (const char *e = getenv("GSPN_BQ_QPW")) {  // tuning door (tools/op_bench.py)
+        int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4) qpw = v;
+    }
     if ((size_t)qpw * nsample * 4 * kBQWarps > 96 * 1024) qpw = 1;
     size_t smem = (size_t)2 * kBQTile * 3 * 4 + (size_t)kBQWarps * qpw * nsample * 4;
     if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;
