@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
     unsigned char *Rg[2] = {sm, sm + p.r0_bytes};
     const uint32_t aring = base + p.r0_bytes + p.r1_bytes;
     const uint32_t wring = aring + (uint32_t)p.a_stages * kTileBytes;
-    float *affine = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes +
-                                              (size_t)p.w_stages * p.stage_bytes);
+    float *xpose = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes +
+                                             (size_t)p.w_stages * p.stage_bytes);  // [4 warps][32][33] output transpose pad
+    float *affine = xpose + (p.pool == 1 ? 4 * 32 * 33 + 12 : 0);  // +12 keeps the affine table 16-byte aligned
     const uint32_t w_full = s_u32(&bars[0]), w_empty = s_u32(&bars[kMaxStages]), a_full = s_u32(&bars[2 * kMaxStages]),
                    a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]);
 
@@ -177,8 +178,13 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
     for (int l = 0; l < p.nlayers; ++l) blocks_per_tile += ((p.N[l] + p.nch - 1) / p.nch) * (p.K[l] >> 6);
     const int kb0 = p.K[0] >> 6;
     const long my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const long total_w = my_tiles * blocks_per_tile, total_a = my_tiles * kb0;
-    long w_issued = 0, w_used = 0, a_issued = 0, a_used = 0;  // ring positions (thread 0 only)
+    const int total_w = (int)(my_tiles * blocks_per_tile), total_a = (int)(my_tiles * kb0);
+    // ring positions (thread 0 only), all incremental: no division on the issue path
+    int w_issued = 0, w_used = 0, a_issued = 0, a_used = 0;
+    int wi_s = 0, wi_par = 0, wu_s = 0, wu_par = 0;  // issue / use stage index and round parity, weights
+    int ai_s = 0, ai_par = 0, au_s = 0, au_par = 0;  // same, layer-0 input blocks
+    long a_tile = blockIdx.x;
+    int a_kb = 0;
     Cursor wc = {0, 0, 0};
     uint32_t done_par = 0;
 
@@ -186,25 +192,22 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
     // while this tile's later layers compute)
     auto top_up = [&]() {
         while (a_issued < total_a && a_issued < a_used + p.a_stages) {
-            const int s = (int)(a_issued % p.a_stages);
-            const long round = a_issued / p.a_stages;
-            if (round > 0) mb_wait(a_empty + 8 * s, (uint32_t)((round - 1) & 1));
-            const long t = blockIdx.x + (a_issued / kb0) * gridDim.x;
-            const int kb = (int)(a_issued % kb0);
-            mb_expect_tx(a_full + 8 * s, kTileBytes);
-            bulk_load(aring + s * kTileBytes, p.a + ((size_t)t * kb0 + kb) * kTileBytes, kTileBytes, a_full + 8 * s);
+            if (a_issued >= p.a_stages) mb_wait(a_empty + 8 * ai_s, (uint32_t)(ai_par ^ 1));
+            mb_expect_tx(a_full + 8 * ai_s, kTileBytes);
+            bulk_load(aring + ai_s * kTileBytes, p.a + ((size_t)a_tile * kb0 + a_kb) * kTileBytes, kTileBytes, a_full + 8 * ai_s);
+            if (++a_kb == kb0) { a_kb = 0; a_tile += gridDim.x; }
+            if (++ai_s == p.a_stages) { ai_s = 0; ai_par ^= 1; }
             ++a_issued;
         }
         while (w_issued < total_w && w_issued < w_used + p.w_stages) {
-            const int s = (int)(w_issued % p.w_stages);
-            const long round = w_issued / p.w_stages;
-            if (round > 0) mb_wait(w_empty + 8 * s, (uint32_t)((round - 1) & 1));
+            if (w_issued >= p.w_stages) mb_wait(w_empty + 8 * wi_s, (uint32_t)(wi_par ^ 1));
             const int rows_i = min(p.nch, p.N[wc.l] - wc.nc * p.nch);
             const uint32_t bytes = (uint32_t)rows_i * 128u;
-            mb_expect_tx(w_full + 8 * s, bytes);
-            bulk_load(wring + s * p.stage_bytes, p.wimg[wc.l] + (size_t)wc.kb * p.N[wc.l] * 128 + (size_t)wc.nc * p.nch * 128, bytes,
-                      w_full + 8 * s);
+            mb_expect_tx(w_full + 8 * wi_s, bytes);
+            bulk_load(wring + wi_s * p.stage_bytes, p.wimg[wc.l] + (size_t)wc.kb * p.N[wc.l] * 128 + (size_t)wc.nc * p.nch * 128, bytes,
+                      w_full + 8 * wi_s);
             wc.advance(p);
+            if (++wi_s == p.w_stages) { wi_s = 0; wi_par ^= 1; }
             ++w_issued;
         }
     };
@@ -219,17 +222,16 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                     uint32_t a_addr;
                     if (l == 0) {
                         top_up();
-                        const int sa = (int)(a_used % p.a_stages);
-                        mb_wait(a_full + 8 * sa, (uint32_t)((a_used / p.a_stages) & 1));
-                        a_addr = aring + sa * kTileBytes;
+                        mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
+                        a_addr = aring + au_s * kTileBytes;
                     } else {
                         a_addr = R[(l - 1) & 1] + kb * kTileBytes;
                     }
                     const uint64_t ad = smem_desc(a_addr);
                     for (int nc = 0; nc < nchunks; ++nc) {
                         top_up();
-                        const int s = (int)(w_used % p.w_stages);
-                        mb_wait(w_full + 8 * s, (uint32_t)((w_used / p.w_stages) & 1));
+                        const int s = wu_s;
+                        mb_wait(w_full + 8 * s, (uint32_t)wu_par);
                         tc_fence_after();
                         const int nrows = min(p.nch, Nl - nc * p.nch);
                         const uint32_t idesc = instr_desc(128, nrows);
@@ -238,10 +240,12 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                         for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
                             tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
                         tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
+                        if (++wu_s == p.w_stages) { wu_s = 0; wu_par ^= 1; }
                         ++w_used;
                     }
                     if (l == 0) {
-                        tc_commit(a_empty + 8 * (int)(a_used % p.a_stages));
+                        tc_commit(a_empty + 8 * au_s);
+                        if (++au_s == p.a_stages) { au_s = 0; au_par ^= 1; }
                         ++a_used;
                     }
                 }
@@ -263,10 +267,17 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                 tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
                 tc_wait_ld();
                 float f[32];
+                {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
+                    const bool relu = p.relu[l] != 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = fmaf(__uint_as_float(v[i]), sc[c0 + i], sh[c0 + i]);
-                    f[i] = p.relu[l] ? fmaxf(x, 0.f) : x;
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 a4 = sc4[g], b4 = sh4[g];  // same address in every lane: one broadcast LDS.128 each
+                        float x0 = fmaf(__uint_as_float(v[4 * g]), a4.x, b4.x), x1 = fmaf(__uint_as_float(v[4 * g + 1]), a4.y, b4.y);
+                        float x2 = fmaf(__uint_as_float(v[4 * g + 2]), a4.z, b4.z), x3 = fmaf(__uint_as_float(v[4 * g + 3]), a4.w, b4.w);
+                        f[4 * g] = relu ? fmaxf(x0, 0.f) : x0; f[4 * g + 1] = relu ? fmaxf(x1, 0.f) : x1;
+                        f[4 * g + 2] = relu ? fmaxf(x2, 0.f) : x2; f[4 * g + 3] = relu ? fmaxf(x3, 0.f) : x3;
+                    }
                 }
                 if (!last) {
 #pragma unroll
@@ -278,12 +289,20 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                                                    (((cc & 7) ^ (row & 7)) << 4)) = pk;
                     }
                 } else if (p.pool == 1) {
-                    if (grow < p.rows) {
-                        if (p.out_f32) {
-                            float4 *o = reinterpret_cast<float4 *>(p.out_f32 + grow * Nl + c0);
+                    if (p.out_f32) {
+                        // thread = row here, but a row's 32 floats are what is contiguous in memory: transpose the
+                        // warp's 32x32 block through its private smem pad so every store instruction writes one full line
+                        float *tp = xpose + warp * (32 * 33);
+                        __syncwarp();
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) o[g] = make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-                        }
+                        for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = f[i];
+                        __syncwarp();
+                        const long r0 = tile * kTileRows + warp * 32;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            if (r0 + r < p.rows) __stcs(p.out_f32 + (r0 + r) * Nl + c0 + lane, tp[r * 33 + lane]);
+                    }
+                    if (grow < p.rows) {
                         if (p.out_bf16) {
                             uint4 *o = reinterpret_cast<uint4 *>(p.out_bf16 + grow * Nl + c0);
 #pragma unroll
@@ -341,13 +360,35 @@ __global__ void __launch_bounds__(256) fp_assemble_kernel(long rows, int n, int 
                                                           const float *__restrict__ weight, unsigned char *__restrict__ img, int ld) {
     const int chunks = ld >> 3;
     const long total = rows * chunks;
+    const bool vec2 = (c2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(points2) & 15u) == 0);
+    const bool vec1 = (c2 % 8 == 0) && (c1 % 4 == 0) && points1 && ((reinterpret_cast<uintptr_t>(points1) & 15u) == 0);
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         long row = e / chunks;
         int ch = (int)(e - row * chunks);
         long bi = row / n;
         float v[8];
         const int col0 = ch * 8;
-        if (col0 < c2) {
+        if (col0 + 8 <= c2 && vec2) {
+            // whole chunk interpolated: 6 x 128-bit gathers; (p1*w1+p2*w2)+p3*w3, no FMA: tf_interpolate.cpp:107-127
+            const int *ip = idx + row * 3;
+            const float *wp = weight + row * 3;
+            const float w1 = __ldg(wp), w2 = __ldg(wp + 1), w3 = __ldg(wp + 2);
+            const float4 *b1 = reinterpret_cast<const float4 *>(points2 + (bi * m + __ldg(ip)) * c2 + col0);
+            const float4 *b2 = reinterpret_cast<const float4 *>(points2 + (bi * m + __ldg(ip + 1)) * c2 + col0);
+            const float4 *b3 = reinterpret_cast<const float4 *>(points2 + (bi * m + __ldg(ip + 2)) * c2 + col0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 a = __ldg(b1 + h), b = __ldg(b2 + h), c = __ldg(b3 + h);
+                v[4 * h] = __fadd_rn(__fadd_rn(__fmul_rn(a.x, w1), __fmul_rn(b.x, w2)), __fmul_rn(c.x, w3));
+                v[4 * h + 1] = __fadd_rn(__fadd_rn(__fmul_rn(a.y, w1), __fmul_rn(b.y, w2)), __fmul_rn(c.y, w3));
+                v[4 * h + 2] = __fadd_rn(__fadd_rn(__fmul_rn(a.z, w1), __fmul_rn(b.z, w2)), __fmul_rn(c.z, w3));
+                v[4 * h + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a.w, w1), __fmul_rn(b.w, w2)), __fmul_rn(c.w, w3));
+            }
+        } else if (col0 >= c2 && col0 - c2 + 8 <= c1 && vec1) {
+            const float4 *q = reinterpret_cast<const float4 *>(points1 + row * c1 + (col0 - c2));
+            const float4 a = __ldg(q), b = __ldg(q + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else if (col0 < c2) {
             const int *ip = idx + row * 3;
             const float *wp = weight + row * 3;
             int i1 = __ldg(ip), i2 = __ldg(ip + 1), i3 = __ldg(ip + 2);
@@ -357,7 +398,6 @@ __global__ void __launch_bounds__(256) fp_assemble_kernel(long rows, int n, int 
             for (int t = 0; t < 8; ++t) {
                 int col = col0 + t;
                 if (col < c2) {
-                    // (p1*w1+p2*w2)+p3*w3, no FMA: tf_interpolate.cpp:107-127
                     v[t] = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(b1 + col), w1), __fmul_rn(__ldg(b2 + col), w2)), __fmul_rn(__ldg(b3 + col), w3));
                 } else {
                     int q = col - c2;
@@ -441,31 +481,39 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     p.r0_bytes = (uint32_t)(rk[0] / 64) * kTileBytes;
     p.r1_bytes = (uint32_t)(rk[1] / 64) * kTileBytes;
     p.stage_bytes = (uint32_t)p.nch * 128u;
-    size_t smem = 0;
+    // ring depths: the deepest rings that still give the best CTA co-residency (a second CTA on the SM overlaps
+    // its MMAs with this one's epilogue); TMEM (512 columns/SM) bounds co-residency too
+    const int occ_tmem = 512 / p.tmem_cols;
+    const size_t fixed = 1024 + (size_t)p.r0_bytes + p.r1_bytes + affine_floats * sizeof(float) + (pool == 1 ? (4 * 32 * 33 + 12) * sizeof(float) : 0);
     const int tries[4][2] = {{3, 4}, {2, 4}, {2, 3}, {2, 2}};
-    bool fits = false;
-    for (int t = 0; t < 4 && !fits; ++t) {
-        p.a_stages = tries[t][0];
-        p.w_stages = tries[t][1];
-        smem = 1024 + (size_t)p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes + (size_t)p.w_stages * p.stage_bytes +
-               affine_floats * sizeof(float);
-        fits = smem <= 227 * 1024;
+    size_t smem = 0;
+    int occ = 0;
+    for (int t = 0; t < 4; ++t) {
+        size_t sz = fixed + (size_t)tries[t][0] * kTileBytes + (size_t)tries[t][1] * p.stage_bytes;
+        if (sz > 227 * 1024) continue;
+        int o = (int)((228 * 1024) / (sz + 1024));
+        o = o > occ_tmem ? occ_tmem : o;
+        o = o > 4 ? 4 : o;
+        if (o > occ) { occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1]; }
     }
-    if (!fits) return GSPN_E_UNSUPPORTED;
-    // TMEM holds 512 columns per SM: keep co-resident CTAs * tmem_cols <= 512 by inflating the smem request
-    int occ_tmem = 512 / p.tmem_cols;
-    size_t min_smem = (size_t)(228 * 1024) / (occ_tmem + 1) + 1;
+    if (occ < 1) return GSPN_E_UNSUPPORTED;
+    // never let more CTAs co-reside than TMEM can serve: inflate the request if shared memory alone would allow it
+    const size_t min_smem = (size_t)(228 * 1024) / (occ + 1) - 1024 + 1;
     if (smem < min_smem) smem = min_smem;
     cudaStream_t s = as_stream(stream);
-    GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    GSPN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mlp_chain_kernel, kTcThreads, smem));
-    if (occ < 1) return GSPN_E_UNSUPPORTED;
-    if (occ > occ_tmem) occ = occ_tmem;
-    int dev = 0, sms = 148;
-    GSPN_CUDA_OK(cudaGetDevice(&dev));
-    GSPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    long grid = (long)sms * occ;
+    static int smem_attr_set = 0;  // launch attribute already raised to at least this (benign race: set is idempotent)
+    if ((int)smem > smem_attr_set) {
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        smem_attr_set = 227 * 1024;
+    }
+    static int sms_cached = 0;
+    if (sms_cached == 0) {
+        int dev = 0, sms = 148;
+        GSPN_CUDA_OK(cudaGetDevice(&dev));
+        GSPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        sms_cached = sms;
+    }
+    long grid = (long)sms_cached * occ;
     if (grid > p.ntiles) grid = p.ntiles;
     if (pool > 1 && pool != 32)
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
