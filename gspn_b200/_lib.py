@@ -46,6 +46,7 @@ SIGNATURES = {
     "gspn_mlp_weight_image_bytes": (c_size_t, [c_int, c_int]),
     "gspn_mlp_pack_weights": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "gspn_mlp_chain": (c_int, [c_long, c_int, P, P, P, P, P, P, c_int, P, P, P]),
+    "gspn_mlp_chain_set_profile": (None, [P]),
     "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
 }
 

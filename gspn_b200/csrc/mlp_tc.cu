@@ -21,7 +21,8 @@
 namespace gspn {
 
 constexpr int kMaxLayers = 4;
-constexpr int kTcThreads = 128;
+constexpr int kMaxEpiWarps = 8;  // 4 or 8 epilogue warps (thread 0 also issues the MMAs) + 2 producer warps
+constexpr int kMaxTcThreads = kMaxEpiWarps * 32 + 64;
 constexpr int kMaxStages = 4;
 
 struct ChainParams {
@@ -40,8 +41,10 @@ struct ChainParams {
     __nv_bfloat16 *out_bf16;
     int nch;  // weight rows (output channels) per ring stage / per MMA
     int tmem_cols;
+    int epi_warps;           // 4, or 8 (two warps per TMEM lane quadrant, each taking half the columns)
     int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
     uint32_t r0_bytes, r1_bytes, stage_bytes;
+    long long *prof;  // optional: per-phase cycle counters of CTA 0 / thread 0 (tools/tc_profile.py)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -121,7 +124,7 @@ struct Cursor {  // position in the per-tile weight block sequence: layer, k-blo
     }
 };
 
-__global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams p) {
+__global__ void __launch_bounds__(kMaxTcThreads) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
     const uint32_t wring = aring + (uint32_t)p.a_stages * kTileBytes;
     float *xpose = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes +
                                              (size_t)p.w_stages * p.stage_bytes);  // [4 warps][32][33] output transpose pad
-    float *affine = xpose + (p.pool == 1 ? 4 * 32 * 33 + 12 : 0);  // +12 keeps the affine table 16-byte aligned
+    float *affine = xpose + (p.pool == 1 ? p.epi_warps * 32 * 33 : 0);  // 32*33*4 bytes per pad keeps 16-byte alignment
     const uint32_t w_full = s_u32(&bars[0]), w_empty = s_u32(&bars[kMaxStages]), a_full = s_u32(&bars[2 * kMaxStages]),
                    a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]);
 
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
         int o = 0;
         for (int l = 0; l < p.nlayers; ++l) {
             aoff[l] = o;
-            for (int i = tid; i < p.N[l]; i += kTcThreads) {
+            for (int i = tid; i < p.N[l]; i += blockDim.x) {
                 affine[o + i] = __ldg(p.scale[l] + i);
                 affine[o + p.N[l] + i] = __ldg(p.shift[l] + i);
             }
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *r = reinterpret_cast<uint4 *>(sm);
-        for (uint32_t i = tid; i < (p.r0_bytes + p.r1_bytes) / 16; i += kTcThreads) r[i] = z;
+        for (uint32_t i = tid; i < (p.r0_bytes + p.r1_bytes) / 16; i += blockDim.x) r[i] = z;
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -179,49 +182,52 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
     const int kb0 = p.K[0] >> 6;
     const long my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int total_w = (int)(my_tiles * blocks_per_tile), total_a = (int)(my_tiles * kb0);
-    // ring positions (thread 0 only), all incremental: no division on the issue path
-    int w_issued = 0, w_used = 0, a_issued = 0, a_used = 0;
-    int wi_s = 0, wi_par = 0, wu_s = 0, wu_par = 0;  // issue / use stage index and round parity, weights
-    int ai_s = 0, ai_par = 0, au_s = 0, au_par = 0;  // same, layer-0 input blocks
-    long a_tile = blockIdx.x;
-    int a_kb = 0;
-    Cursor wc = {0, 0, 0};
-    uint32_t done_par = 0;
 
-    // thread 0: keep both rings full; they run ahead across layers and tiles (next tile's input prefetches
-    // while this tile's later layers compute)
-    auto top_up = [&]() {
-        while (a_issued < total_a && a_issued < a_used + p.a_stages) {
-            if (a_issued >= p.a_stages) mb_wait(a_empty + 8 * ai_s, (uint32_t)(ai_par ^ 1));
-            mb_expect_tx(a_full + 8 * ai_s, kTileBytes);
-            bulk_load(aring + ai_s * kTileBytes, p.a + ((size_t)a_tile * kb0 + a_kb) * kTileBytes, kTileBytes, a_full + 8 * ai_s);
-            if (++a_kb == kb0) { a_kb = 0; a_tile += gridDim.x; }
-            if (++ai_s == p.a_stages) { ai_s = 0; ai_par ^= 1; }
-            ++a_issued;
+    // ---- producer warps: one lane each keeps a ring full for the whole kernel, independent of the MMA/epilogue
+    // timeline, so the loads of the next layers / tiles are in flight while the epilogue warps are busy
+    if (warp == p.epi_warps) {
+        if (lane == 0) {
+            int s = 0, par = 0, kb = 0;
+            long t = blockIdx.x;
+            for (int i = 0; i < total_a; ++i) {
+                if (i >= p.a_stages) mb_wait(a_empty + 8 * s, (uint32_t)(par ^ 1));
+                mb_expect_tx(a_full + 8 * s, kTileBytes);
+                bulk_load(aring + s * kTileBytes, p.a + ((size_t)t * kb0 + kb) * kTileBytes, kTileBytes, a_full + 8 * s);
+                if (++kb == kb0) { kb = 0; t += gridDim.x; }
+                if (++s == p.a_stages) { s = 0; par ^= 1; }
+            }
         }
-        while (w_issued < total_w && w_issued < w_used + p.w_stages) {
-            if (w_issued >= p.w_stages) mb_wait(w_empty + 8 * wi_s, (uint32_t)(wi_par ^ 1));
-            const int rows_i = min(p.nch, p.N[wc.l] - wc.nc * p.nch);
-            const uint32_t bytes = (uint32_t)rows_i * 128u;
-            mb_expect_tx(w_full + 8 * wi_s, bytes);
-            bulk_load(wring + wi_s * p.stage_bytes, p.wimg[wc.l] + (size_t)wc.kb * p.N[wc.l] * 128 + (size_t)wc.nc * p.nch * 128, bytes,
-                      w_full + 8 * wi_s);
-            wc.advance(p);
-            if (++wi_s == p.w_stages) { wi_s = 0; wi_par ^= 1; }
-            ++w_issued;
+    } else if (warp == p.epi_warps + 1) {
+        if (lane == 0) {
+            int s = 0, par = 0;
+            Cursor wc = {0, 0, 0};
+            for (int i = 0; i < total_w; ++i) {
+                if (i >= p.w_stages) mb_wait(w_empty + 8 * s, (uint32_t)(par ^ 1));
+                const int rows_i = min(p.nch, p.N[wc.l] - wc.nc * p.nch);
+                const uint32_t bytes = (uint32_t)rows_i * 128u;
+                mb_expect_tx(w_full + 8 * s, bytes);
+                bulk_load(wring + s * p.stage_bytes, p.wimg[wc.l] + (size_t)wc.kb * p.N[wc.l] * 128 + (size_t)wc.nc * p.nch * 128, bytes,
+                          w_full + 8 * s);
+                wc.advance(p);
+                if (++s == p.w_stages) { s = 0; par ^= 1; }
+            }
         }
-    };
+    } else {
+    // ---- MMA issue (thread 0) + epilogue (warps 0-3)
+    int wu_s = 0, wu_par = 0, au_s = 0, au_par = 0;  // consumer-side stage index and round parity
+    uint32_t done_par = 0;
 
     for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         for (int l = 0; l < p.nlayers; ++l) {
             const int Nl = p.N[l], KBl = p.K[l] >> 6;
+            long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
+            if (p.prof) pt0 = clock64();
             if (tid == 0) {
                 tc_fence_after();
                 const int nchunks = (Nl + p.nch - 1) / p.nch;
                 for (int kb = 0; kb < KBl; ++kb) {
                     uint32_t a_addr;
                     if (l == 0) {
-                        top_up();
                         mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
                         a_addr = aring + au_s * kTileBytes;
                     } else {
@@ -229,7 +235,6 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                     }
                     const uint64_t ad = smem_desc(a_addr);
                     for (int nc = 0; nc < nchunks; ++nc) {
-                        top_up();
                         const int s = wu_s;
                         mb_wait(w_full + 8 * s, (uint32_t)wu_par);
                         tc_fence_after();
@@ -241,31 +246,31 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                             tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
                         tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
                         if (++wu_s == p.w_stages) { wu_s = 0; wu_par ^= 1; }
-                        ++w_used;
                     }
                     if (l == 0) {
                         tc_commit(a_empty + 8 * au_s);
                         if (++au_s == p.a_stages) { au_s = 0; au_par ^= 1; }
-                        ++a_used;
                     }
                 }
                 tc_commit(mma_done);
             }
             __syncwarp();
+            if (p.prof) pt1 = clock64();
             mb_wait(mma_done, done_par);
             done_par ^= 1;
             tc_fence_after();
+            if (p.prof) pt2 = clock64();
 
             // ---- epilogue: thread = row (TMEM lane), 32 columns at a time
             const bool last = (l == p.nlayers - 1);
             const float *sc = affine + aoff[l], *sh = sc + Nl;
-            const int row = warp * 32 + lane;
+            const int quad = warp & 3, half = warp >> 2, nhalf = p.epi_warps >> 2;
+            const int row = quad * 32 + lane;
             const long grow = tile * kTileRows + row;
+            const int c_lo = ((Nl >> 5) * half / nhalf) << 5, c_hi = ((Nl >> 5) * (half + 1) / nhalf) << 5;  // this warp's columns
             unsigned char *outb = Rg[l & 1];
-            for (int c0 = 0; c0 < Nl; c0 += 32) {
-                uint32_t v[32];
-                tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-                tc_wait_ld();
+            const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16);
+            auto process = [&](const uint32_t (&v)[32], const int c0) {
                 float f[32];
                 {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
@@ -292,12 +297,12 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                     if (p.out_f32) {
                         // thread = row here, but a row's 32 floats are what is contiguous in memory: transpose the
                         // warp's 32x32 block through its private smem pad so every store instruction writes one full line
-                        float *tp = xpose + warp * (32 * 33);
+                        float *tp = xpose + warp * (32 * 33);  // one pad per epilogue warp
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = f[i];
                         __syncwarp();
-                        const long r0 = tile * kTileRows + warp * 32;
+                        const long r0 = tile * kTileRows + quad * 32;
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r)
                             if (r0 + r < p.rows) __stcs(p.out_f32 + (r0 + r) * Nl + c0 + lane, tp[r * 33 + lane]);
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                         int mx = __reduce_max_sync(GSPN_FULL_MASK, __float_as_int(f[i]));
                         if (lane == i) keep = mx;
                     }
-                    const long row0 = tile * kTileRows + warp * 32;
+                    const long row0 = tile * kTileRows + quad * 32;
                     if (row0 < p.rows) {
                         const long grp = row0 / p.pool;
                         if (p.pool == 32) {
@@ -330,12 +335,37 @@ __global__ void __launch_bounds__(kTcThreads) mlp_chain_kernel(const ChainParams
                         }
                     }
                 }
+            };
+            // software-pipelined TMEM reads: the load of the next 32 columns is in flight while this one is processed
+            {
+                uint32_t va[32], vb[32];
+                if (c_lo < c_hi) tc_ld32(tbase + c_lo, va);
+                for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
+                    tc_wait_ld();
+                    if (c0 + 32 < c_hi) tc_ld32(tbase + c0 + 32, vb);
+                    process(va, c0);
+                    if (c0 + 32 < c_hi) {
+                        tc_wait_ld();
+                        if (c0 + 64 < c_hi) tc_ld32(tbase + c0 + 64, va);
+                        process(vb, c0 + 32);
+                    }
+                }
             }
+            if (p.prof) pt3 = clock64();
             tc_fence_before();
             fence_proxy_async();  // epilogue st.shared -> visible to the tensor core's async-proxy reads
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"r"(p.epi_warps * 32) : "memory");  // the epilogue warps only; producers run free
+            if (p.prof && blockIdx.x == 0 && tid == 0) {
+                long long pt4 = clock64();
+                atomicAdd((unsigned long long *)p.prof + 0, (unsigned long long)(pt1 - pt0));  // issue (loads + MMAs)
+                atomicAdd((unsigned long long *)p.prof + 1, (unsigned long long)(pt2 - pt1));  // wait for MMA completion
+                atomicAdd((unsigned long long *)p.prof + 2, (unsigned long long)(pt3 - pt2));  // epilogue
+                atomicAdd((unsigned long long *)p.prof + 3, (unsigned long long)(pt4 - pt3));  // fences + CTA barrier
+                atomicAdd((unsigned long long *)p.prof + 4, 1ull);                              // layer-steps
+            }
         }
     }
+    }  // roles
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
 }
@@ -435,6 +465,9 @@ extern "C" int gspn_mlp_pack_weights(int cin, int cin_padded, int cout, const fl
     return check_launch();
 }
 
+static long long *g_chain_prof = nullptr;  // tuning door: set by gspn_mlp_chain_set_profile, read at launch
+extern "C" void gspn_mlp_chain_set_profile(long long *prof5) { g_chain_prof = prof5; }
+
 extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a, const void *const *wimg, const float *const *scale,
                               const float *const *shift, const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream) {
     GSPN_REQUIRE(rows >= 0 && nlayers >= 1 && nlayers <= kMaxLayers && pool >= 1);
@@ -466,6 +499,7 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
         if (pool != 32 && (out_f32 == nullptr || out_bf16 != nullptr)) return GSPN_E_UNSUPPORTED;
     }
     p.a = (const unsigned char *)a;
+    p.prof = g_chain_prof;
     p.pool = pool;
     p.out_f32 = out_f32;
     p.out_bf16 = (__nv_bfloat16 *)out_bf16;
@@ -484,16 +518,16 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     // ring depths: the deepest rings that still give the best CTA co-residency (a second CTA on the SM overlaps
     // its MMAs with this one's epilogue); TMEM (512 columns/SM) bounds co-residency too
     const int occ_tmem = 512 / p.tmem_cols;
-    const size_t fixed = 1024 + (size_t)p.r0_bytes + p.r1_bytes + affine_floats * sizeof(float) + (pool == 1 ? (4 * 32 * 33 + 12) * sizeof(float) : 0);
+    const size_t fixed = 1024 + (size_t)p.r0_bytes + p.r1_bytes + affine_floats * sizeof(float) + (pool == 1 ? (8 * 32 * 33) * sizeof(float) : 0);
     const int tries[4][2] = {{3, 4}, {2, 4}, {2, 3}, {2, 2}};
     size_t smem = 0;
     int occ = 0;
     for (int t = 0; t < 4; ++t) {
         size_t sz = fixed + (size_t)tries[t][0] * kTileBytes + (size_t)tries[t][1] * p.stage_bytes;
-        if (sz > 227 * 1024) continue;
+        if (sz > 226 * 1024) continue;
         int o = (int)((228 * 1024) / (sz + 1024));
         o = o > occ_tmem ? occ_tmem : o;
-        o = o > 4 ? 4 : o;
+        o = o > 2 ? 2 : o;  // 168 registers x 192 threads: two CTAs fill the register file
         if (o > occ) { occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1]; }
     }
     if (occ < 1) return GSPN_E_UNSUPPORTED;
@@ -503,8 +537,9 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     cudaStream_t s = as_stream(stream);
     static int smem_attr_set = 0;  // launch attribute already raised to at least this (benign race: set is idempotent)
     if ((int)smem > smem_attr_set) {
-        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        smem_attr_set = 227 * 1024;
+        // 227 KiB is the per-CTA limit for static + dynamic together; leave 1 KiB for the kernel's static __shared__
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        smem_attr_set = 226 * 1024;
     }
     static int sms_cached = 0;
     if (sms_cached == 0) {
@@ -517,7 +552,9 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     if (grid > p.ntiles) grid = p.ntiles;
     if (pool > 1 && pool != 32)
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
-    mlp_chain_kernel<<<(unsigned)grid, kTcThreads, smem, s>>>(p);
+    // one CTA per SM (shared-memory bound): give it 8 epilogue warps; two CTAs per SM: 4 each (register file)
+    p.epi_warps = occ >= 2 ? 4 : 8;
+    mlp_chain_kernel<<<(unsigned)grid, p.epi_warps * 32 + 64, smem, s>>>(p);
     return check_launch();
 }
 

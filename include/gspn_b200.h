@@ -168,6 +168,11 @@ int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a,
                    const void *const *wimg, const float *const *scale, const float *const *shift,
                    const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream);
 
+/* Tuning door: when prof5 (device, 5 x int64, zeroed by the caller) is non-NULL, later gspn_mlp_chain launches add
+ * CTA 0 / thread 0's cycle counts: [0] load+MMA issue, [1] MMA completion wait, [2] epilogue, [3] fences+barrier,
+ * [4] number of layer-steps.  NULL switches it off. */
+void gspn_mlp_chain_set_profile(long long *prof5);
+
 /* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of
  * points2 (b,m,c2) with idx/weight (b,n,3), concatenated with points1 (b,n,c1) (may be NULL, c1=0),
  * written straight into the bf16 tile image (ld = 64*ceil((c1+c2)/64)) for gspn_mlp_chain. */
