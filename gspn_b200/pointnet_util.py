@@ -29,7 +29,7 @@ from . import ops
 
 BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (utils/tf_util.py:530-534)
 
-DEFAULT_PRECISION = "fp32"
+DEFAULT_PRECISION = "bf16"  # the north-star path (tcgen05); pass precision="fp32" for reference-precision MLPs
 
 
 class VariableStore(dict):
