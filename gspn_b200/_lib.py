@@ -31,12 +31,13 @@ SIGNATURES = {
     "gspn_fps_profile": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P]),
     "gspn_gather_point": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_gather_point_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
-    "gspn_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, P, P, P, P, P]),
+    "gspn_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gspn_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, P, P, P, P, P, c_size_t, P]),
     "gspn_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_grouped_bytes": (c_size_t, [c_long, c_int, c_int]),
-    "gspn_ballquery_group": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, P, c_int, P, P, P, c_int, c_int, P]),
-    "gspn_three_nn": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P]),
+    "gspn_ballquery_group": (c_int, [c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, P, c_int, P, P, P, c_int, c_int, P, c_size_t, P]),
+    "gspn_three_nn": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "gspn_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "gspn_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "gspn_nn_distance": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_int, P]),

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "common.cuh"
+#include "group_rows.cuh"
 
 namespace gspn {
 
@@ -65,96 +66,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-struct GroupArgs {
-    const float *shift;  // optional (b,m,3) extra shift (multi_encoding_net, model_rpointnet.py:56-57)
-    const void *points;          // (b,n,c) f32 or bf16, may be null
-    int c;
-    int points_bf16;
-    void *grouped;  // null -> indices only
-    int grouped_bf16;
-    int ld;
-};
-
-// one element of a neighbourhood row: [ features(c) | (xyz - centre) - shift | 0 ]
-struct RowSrc {
-    const float *pts_f;
-    const __nv_bfloat16 *pts_h;
-    const float *xyz;  // cloud base
-    int c;
-    float qx, qy, qz, sx, sy, sz;
-    bool has_shift;
-    __device__ __forceinline__ float at(int ii, int col) const {
-        if (col < c) {
-            size_t o = (size_t)ii * c + col;
-            return pts_h ? __bfloat162float(pts_h[o]) : __ldg(pts_f + o);
-        }
-        if (col < c + 3) {
-            int a = col - c;
-            float q = a == 0 ? qx : (a == 1 ? qy : qz);
-            float v = __fsub_rn(__ldg(xyz + (size_t)ii * 3 + a), q);  // grouped_xyz -= new_xyz (pointnet_util.py:42)
-            if (has_shift) v = __fsub_rn(v, a == 0 ? sx : (a == 1 ? sy : sz));  // -= shift_pred (model_rpointnet.py:56-57)
-            return v;
-        }
-        return 0.f;
-    }
-};
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-
-// write one neighbourhood (nsample rows) of query (cloud,j); sidx = the row's indices in smem
-__device__ __forceinline__ void write_group(const GroupArgs &g, int n, int m, int nsample, int cloud, int j, const int *sidx,
-                                            const float *__restrict__ xyz, float qx, float qy, float qz, int lane) {
-    const long row0 = ((long)cloud * m + j) * nsample;
-    RowSrc src;
-    src.c = g.c;
-    src.pts_f = g.points_bf16 ? nullptr : (const float *)g.points + (size_t)cloud * n * g.c;
-    src.pts_h = g.points_bf16 ? (const __nv_bfloat16 *)g.points + (size_t)cloud * n * g.c : nullptr;
-    src.xyz = xyz + (size_t)cloud * n * 3;
-    src.qx = qx; src.qy = qy; src.qz = qz;
-    src.has_shift = g.shift != nullptr;
-    src.sx = src.sy = src.sz = 0.f;
-    if (src.has_shift) {
-        const float *sp = g.shift + ((size_t)cloud * m + j) * 3;
-        src.sx = __ldg(sp); src.sy = __ldg(sp + 1); src.sz = __ldg(sp + 2);
-    }
-    if (!g.grouped_bf16) {
-        // lanes sweep the (row, column) space of the block; columns are contiguous in memory
-        float *out = (float *)g.grouped;
-        const int ld = g.ld;
-        for (int e = lane; e < nsample * ld; e += 32) {
-            int s = e / ld, col = e - s * ld;
-            out[(row0 + s) * ld + col] = src.at(sidx[s], col);
-        }
-        return;
-    }
-    // bf16 tile image: one 16-byte chunk (8 columns) per lane-step
-    unsigned char *img = (unsigned char *)g.grouped;
-    const int chunks = g.ld >> 3;
-    const bool vec_f = src.pts_f && (g.c % 4 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_f) & 15u) == 0);
-    const bool vec_h = src.pts_h && (g.c % 8 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_h) & 15u) == 0);
-    for (int e = lane; e < nsample * chunks; e += 32) {
-        int s = e / chunks, ch = e - s * chunks;
-        int ii = sidx[s];
-        uint4 pk;
-        if (ch * 8 + 8 <= g.c && vec_h) {
-            pk = __ldg(reinterpret_cast<const uint4 *>(src.pts_h + (size_t)ii * g.c + ch * 8));
-        } else if (ch * 8 + 8 <= g.c && vec_f) {
-            const float4 *fp = reinterpret_cast<const float4 *>(src.pts_f + (size_t)ii * g.c + ch * 8);
-            float4 a = __ldg(fp), b = __ldg(fp + 1);
-            pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
-        } else {
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = src.at(ii, ch * 8 + t);
-            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-        }
-        *reinterpret_cast<uint4 *>(img + tile_chunk_offset(row0 + s, ch, g.ld)) = pk;
-    }
 }
 
 // grid = (ceil(m / (kBQWarps*QPW)), b).  dynamic smem: 2 point tiles + per-warp index rows.
@@ -282,6 +193,12 @@ __global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, flo
 
 using namespace gspn;
 
+// grid_search.cu
+int gspn_ballquery_grid_launch(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
+                               GroupArgs ga, void *workspace, cudaStream_t s);
+extern "C" size_t gspn_grid_workspace_bytes(int b, int n);
+constexpr int kGridMinPoints = 4096;  // below this the brute-force scan is already a few microseconds
+
 static int launch_ballquery(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
                             GroupArgs g, cudaStream_t s) {
     const float s_max = ball_threshold(radius);
@@ -310,12 +227,16 @@ static int launch_ballquery(int b, int n, int m, float radius, int nsample, cons
 }
 
 extern "C" int gspn_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx,
-                                     int *pts_cnt, gspn_stream_t stream) {
+                                     int *pts_cnt, void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
     GSPN_REQUIRE(radius > 0.f && nsample > 0);  // tf_grouping.cpp:101,104
     GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && b <= 65535);  // :109-114
     if (b == 0 || m == 0) return GSPN_OK;
     GSPN_REQUIRE_PTR(xyz1); GSPN_REQUIRE_PTR(xyz2); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(pts_cnt);
     GroupArgs g = {};
+    if (workspace != nullptr && n >= kGridMinPoints && std::isfinite(radius)) {
+        if (workspace_bytes < gspn_grid_workspace_bytes(b, n)) return GSPN_E_WORKSPACE;
+        return gspn_ballquery_grid_launch(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, g, workspace, as_stream(stream));
+    }
     return launch_ballquery(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, g, as_stream(stream));
 }
 
@@ -331,7 +252,7 @@ extern "C" size_t gspn_grouped_bytes(long rows, int c_plus_xyz, int grouped_dtyp
 
 extern "C" int gspn_ballquery_group(int b, int n, int m, int c, float radius, int nsample, const float *xyz, const float *new_xyz,
                                     const float *shift, const void *points, int points_dtype, int *idx, int *pts_cnt, void *grouped,
-                                    int grouped_dtype, int ld, gspn_stream_t stream) {
+                                    int grouped_dtype, int ld, void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
     GSPN_REQUIRE(radius > 0.f && nsample > 0);
     GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && b <= 65535);
     if (points_dtype != GSPN_DT_F32 && points_dtype != GSPN_DT_BF16) return GSPN_E_BAD_DTYPE;
@@ -349,5 +270,9 @@ extern "C" int gspn_ballquery_group(int b, int n, int m, int c, float radius, in
     g.grouped = grouped;
     g.grouped_bf16 = grouped_dtype == GSPN_DT_BF16;
     g.ld = ld;
+    if (workspace != nullptr && n >= kGridMinPoints && std::isfinite(radius)) {
+        if (workspace_bytes < gspn_grid_workspace_bytes(b, n)) return GSPN_E_WORKSPACE;
+        return gspn_ballquery_grid_launch(b, n, m, radius, nsample, xyz, new_xyz, idx, pts_cnt, g, workspace, as_stream(stream));
+    }
     return launch_ballquery(b, n, m, radius, nsample, xyz, new_xyz, idx, pts_cnt, g, as_stream(stream));
 }

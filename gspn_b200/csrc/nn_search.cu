@@ -145,12 +145,21 @@ static void launch_nn(int b, int n, int m, const float *xyz1, const float *xyz2,
 
 using namespace gspn;
 
+// grid_search.cu
+int gspn_three_nn_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight, void *workspace,
+                              cudaStream_t s);
+extern "C" size_t gspn_grid_workspace_bytes(int b, int n);
+
 extern "C" int gspn_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight,
-                             gspn_stream_t stream) {
+                             void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
     GSPN_REQUIRE(b >= 0 && n >= 0 && m > 0 && b <= 65535);  // tf_interpolate.cpp:163-169
     if (b == 0 || n == 0) return GSPN_OK;
     GSPN_REQUIRE_PTR(xyz1); GSPN_REQUIRE_PTR(xyz2); GSPN_REQUIRE_PTR(dist); GSPN_REQUIRE_PTR(idx);
     cudaStream_t s = as_stream(stream);
+    if (workspace != nullptr && m >= 1024 && (long)n * m >= (1L << 22)) {  // grid over the known points
+        if (workspace_bytes < gspn_grid_workspace_bytes(b, m)) return GSPN_E_WORKSPACE;
+        return gspn_three_nn_grid_launch(b, n, m, xyz1, xyz2, dist, idx, weight, workspace, s);
+    }
     if ((long)b * n >= 148L * 8 * kNNThreads * 2) {
         dim3 grid(ceil_div(n, kNNThreads * 2), b);
         three_nn_kernel<2><<<grid, kNNThreads, 0, s>>>(n, m, xyz1, xyz2, dist, idx, weight);

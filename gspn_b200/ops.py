@@ -54,6 +54,17 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+GRID_SEARCH = True  # exact uniform-grid neighbour search for large clouds (False: always the O(n*m) scans)
+
+
+def _grid_ws(b, n_scanned, dev, min_points):
+    """Workspace for the grid search, or (None, 0) when the cloud is small enough for the plain scan."""
+    if not GRID_SEARCH or n_scanned < min_points:
+        return None, 0
+    nbytes = _lib.lib().gspn_grid_workspace_bytes(b, n_scanned)
+    return torch.empty((nbytes,), dtype=torch.uint8, device=dev), nbytes
+
+
 # ----------------------------------------------------------------------------- sampling
 def farthest_point_sample(npoint, inp):
     """inp (b,n,3) f32 -> (b,npoint) i32; bit-identical to farthestpointsamplingKernel."""
@@ -109,7 +120,8 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     m = xyz2.shape[1]
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
-    check(_lib.lib().gspn_query_ball_point(b, n, m, float(radius), nsample, _p(xyz1), _p(xyz2), _p(idx), _p(cnt), _stream()),
+    ws, wsb = _grid_ws(b, n, xyz1.device, 4096)
+    check(_lib.lib().gspn_query_ball_point(b, n, m, float(radius), nsample, _p(xyz1), _p(xyz2), _p(idx), _p(cnt), _p(ws), wsb, _stream()),
           "query_ball_point")
     return idx, cnt
 
@@ -154,7 +166,8 @@ def three_nn(xyz1, xyz2, return_weight=False):
     dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
     idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
     w = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device) if return_weight else None
-    check(_lib.lib().gspn_three_nn(b, n, m, _p(xyz1), _p(xyz2), _p(dist), _p(idx), _p(w), _stream()), "three_nn")
+    ws, wsb = _grid_ws(b, m, xyz1.device, 1024)
+    check(_lib.lib().gspn_three_nn(b, n, m, _p(xyz1), _p(xyz2), _p(dist), _p(idx), _p(w), _p(ws), wsb, _stream()), "three_nn")
     return (dist, idx, w) if return_weight else (dist, idx)
 
 
@@ -271,8 +284,9 @@ def ballquery_group(radius, nsample, xyz, new_xyz, points, grouped_dtype=torch.f
         gdt = GSPN_DT_F32
         ld = c + 3
         grouped = torch.empty((rows, ld), dtype=torch.float32, device=xyz.device)
+    ws, wsb = _grid_ws(b, n, xyz.device, 4096)
     check(L.gspn_ballquery_group(b, n, m, c, float(radius), nsample, _p(xyz), _p(new_xyz), _p(shift), _p(points), pdt,
-                                 _p(idx), _p(cnt), _p(grouped), gdt, ld, _stream()), "ballquery_group")
+                                 _p(idx), _p(cnt), _p(grouped), gdt, ld, _p(ws), wsb, _stream()), "ballquery_group")
     return idx, cnt, grouped, ld
 
 

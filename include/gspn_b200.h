@@ -86,9 +86,12 @@ int gspn_gather_point_grad(int b, int n, int m, int c, const float *out_g, const
  *   queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt)  tf_grouping_g.cu:186
  * xyz1 (b,n,3) dataset, xyz2 (b,m,3) queries -> idx (b,m,nsample) i32, pts_cnt (b,m) i32.
  * First nsample hits in index order, first hit back-fills the row; a row with
- * no hit (unwritten by the reference) is zero. */
+ * no hit (unwritten by the reference) is zero.
+ * workspace (optional): gspn_grid_workspace_bytes(b, n) bytes.  With it, clouds of >= 4096 points are searched
+ * through a per-cloud uniform grid instead of the O(n*m) scan -- identical results. */
+size_t gspn_grid_workspace_bytes(int b, int npoints_scanned);
 int gspn_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
-                          int *idx, int *pts_cnt, gspn_stream_t stream);
+                          int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes, gspn_stream_t stream);
 /* group_point(points, idx)  tf_grouping.py:54-62; groupPointLauncher tf_grouping_g.cu:194
  * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */
 int gspn_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out, gspn_stream_t stream);
@@ -111,14 +114,17 @@ int gspn_ballquery_group(int b, int n, int m, int c, float radius, int nsample,
                          const float *xyz, const float *new_xyz, const float *shift,
                          const void *points, int points_dtype,
                          int *idx, int *pts_cnt, void *grouped, int grouped_dtype, int ld,
-                         gspn_stream_t stream);
+                         void *workspace, size_t workspace_bytes, gspn_stream_t stream);
 
 /* ------------------------------------------------------------- interpolation
  * three_nn(xyz1, xyz2)  tf_ops/3d_interpolation/tf_interpolate.py:8-17; threenn_cpu tf_interpolate.cpp:60
  * xyz1 (b,n,3) unknown, xyz2 (b,m,3) known -> dist (b,n,3) squared f32 ascending, idx (b,n,3) i32.
  * If weight != NULL also writes the inverse-distance weights of
- * pointnet_fp_module (utils/pointnet_util.py:157-160) so no elementwise pass is needed. */
-int gspn_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight, gspn_stream_t stream);
+ * pointnet_fp_module (utils/pointnet_util.py:157-160) so no elementwise pass is needed.
+ * workspace (optional): gspn_grid_workspace_bytes(b, m) bytes; with it and m >= 1024 the known points are
+ * bucketed in a uniform grid and each query visits a growing block of cells -- identical results. */
+int gspn_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight,
+                  void *workspace, size_t workspace_bytes, gspn_stream_t stream);
 /* three_interpolate(points, idx, weight)  tf_interpolate.py:19-28; threeinterpolate_cpu tf_interpolate.cpp:107
  * points (b,m,c), idx (b,n,3), weight (b,n,3) -> out (b,n,c); (p1*w1+p2*w2)+p3*w3 without FMA. */
 int gspn_three_interpolate(int b, int m, int c, int n, const float *points, const int *idx, const float *weight, float *out, gspn_stream_t stream);

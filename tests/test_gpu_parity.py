@@ -536,3 +536,62 @@ def test_backbone_end_to_end_vs_oracle(cuda, oracle, precision, tol):
     for lvl in range(1, 5):
         assert relerr(N(got["points"][lvl]), exp["points"][lvl]) < tol
     assert relerr(N(got["l0_points"]), exp["l0_points"]) < tol
+
+
+# ------------------------------------------------------------------------------------ uniform-grid search == ordered scans
+GRID_BALL = [
+    ("scene_r02", lambda: scenes.scannet_like_batch(50, 2, 16384)[0], 512, 0.2, 32),
+    ("scene_r05_k256_dense_fallback", lambda: scenes.scannet_like_batch(51, 2, 16384)[0], 128, 0.5, 256),
+    ("scene_r15_k512", lambda: scenes.scannet_like_batch(52, 1, 16384)[0], 64, 1.5, 512),
+    ("cube_dups_unaligned", lambda: scenes.with_duplicates(scenes.uniform_cube(3, 5001, seed=61), 0.4), 300, 0.07, 16),
+    ("tiny_radius", lambda: scenes.uniform_cube(2, 6000, seed=62), 200, 0.004, 8),
+    ("flat_cloud", lambda: scenes.uniform_cube(2, 8192, seed=63) * np.array([1, 1, 0], np.float32), 256, 0.05, 32),
+    ("all_same_point", lambda: np.ones((1, 4500, 3), np.float32), 10, 0.1, 32),
+]
+
+
+@pytest.mark.parametrize("name,make,m,r,k", GRID_BALL, ids=[c[0] for c in GRID_BALL])
+def test_grid_ball_query_equals_ordered_scan(cuda, oracle, name, make, m, r, k):
+    xyz = make()
+    q = oracle.gather_point(xyz, oracle.farthest_point_sample(m, xyz))
+    q[:, -3:] += 0.5 * r  # a few queries that are not dataset points
+    q[:, -1] += 100.0     # and one far outside the bounding box
+    x, qq = T(xyz, cuda), T(q, cuda)
+    assert ops.GRID_SEARCH
+    gi, gc = gspn_b200.query_ball_point(r, k, x, qq)
+    ops.GRID_SEARCH = False
+    try:
+        si, sc = gspn_b200.query_ball_point(r, k, x, qq)
+    finally:
+        ops.GRID_SEARCH = True
+    assert np.array_equal(N(gc), N(sc)) and np.array_equal(N(gi), N(si))
+    ei, ec = oracle.query_ball_point(r, k, xyz[:1], q[:1])
+    assert np.array_equal(N(gc)[:1], ec) and np.array_equal(N(gi)[:1], ei)
+
+
+@pytest.mark.parametrize("name", ["scene", "dups", "clustered_known", "unknown_outside", "flat"])
+def test_grid_three_nn_equals_ordered_scan(cuda, oracle, name):
+    rng = np.random.RandomState(5)
+    xyz1 = scenes.scannet_like_batch(60, 2, 20000)[0]
+    xyz2 = oracle.gather_point(xyz1, oracle.farthest_point_sample(3000, xyz1))
+    if name == "dups":
+        xyz2 = scenes.with_duplicates(xyz2, 0.5)
+        xyz1[:, :2000] = xyz2[:, :2000]
+    elif name == "clustered_known":  # most known points in one corner: queries elsewhere must grow their block
+        xyz2 = (xyz2 * np.float32(0.05)).astype(np.float32)
+        xyz2[:, :20] = xyz1[:, :20]
+    elif name == "unknown_outside":
+        xyz1 = (xyz1 + rng.randn(*xyz1.shape).astype(np.float32) * 3).astype(np.float32)
+    elif name == "flat":
+        xyz1[..., 2] = 1.0
+        xyz2[..., 2] = 1.0
+    a, b = T(xyz1, cuda), T(xyz2, cuda)
+    gd, gi = gspn_b200.three_nn(a, b)
+    ops.GRID_SEARCH = False
+    try:
+        sd, si = gspn_b200.three_nn(a, b)
+    finally:
+        ops.GRID_SEARCH = True
+    assert np.array_equal(N(gi), N(si)) and np.array_equal(bits(N(gd)), bits(N(sd)))
+    ed, ei = oracle.three_nn(xyz1[:1], xyz2[:1])
+    assert np.array_equal(N(gi)[:1], ei) and np.array_equal(bits(N(gd)[:1]), bits(ed))
