@@ -1,0 +1,48 @@
+"""multi_encoding_net -- the GSPN multi-radius context encoder (models/model_rpointnet.py:28-77, called at :377 with
+radius_list=[0.5,1.0,1.5], nsample_list=[256,256,512], mlp_list=[[64,128,256]]*3, mlp_list2=[], use_xyz=True,
+fps_idx=ind_seed, shift_pred=stop_gradient(...)).  SURVEY.md 8f rank 2 / BASELINE config 3.
+
+Per radius: query_ball_point -> group_point(xyz) - new_xyz - shift_pred -> group_point(points) ->
+concat([grouped_points, grouped_xyz]) (points FIRST -- the opposite of sample_and_group, and exactly the column
+order of this library's fused grouping kernel, so no weight permutation is needed) -> conv2d x len(mlp) ->
+reduce_max; results concatenated over radii.  mlp_list2 (conv1d) and output_shift are model-head code outside
+the SA/FP path and are not built (the reference call site passes mlp_list2=[] and output_shift=False).
+"""
+import torch
+
+from . import mlp_tc, ops
+from . import pointnet_util as pu
+
+
+def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list, mlp_list2, is_training, bn_decay, scope, bn=True,
+                       use_xyz=False, output_shift=False, shift_pred=None, fps_idx=None, variables=None, precision=None):
+    """-> (new_xyz (b,npoint,3), new_points (b,npoint,sum mlp[-1]), shift_pred, fps_idx)."""
+    pu._check_unbuilt(is_training)
+    if mlp_list2 or output_shift:
+        raise NotImplementedError("mlp_list2 / output_shift are conv1d head code outside the SA/FP path (reference call site uses neither)")
+    store = pu.VARIABLES if variables is None else variables
+    precision = precision or pu.DEFAULT_PRECISION
+    b, n, _ = xyz.shape
+    if fps_idx is None:
+        fps_idx = ops.farthest_point_sample(npoint, xyz)
+    new_xyz = ops.gather_point(xyz, fps_idx)
+    m = new_xyz.shape[1]
+    c = 0 if points is None else points.shape[2]
+    cin = c + 3 if (use_xyz or points is None) else c
+    outs = []
+    for i, (radius, nsample, mlp) in enumerate(zip(radius_list, nsample_list, mlp_list)):
+        layers = store.layers(scope, "conv_prev_%d_" % i, cin, list(mlp), bn)
+        rows = b * m * nsample
+        if precision == "bf16" and mlp_tc.tc_supported(layers, nsample):
+            idx, _, img, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.bfloat16, shift=shift_pred)
+            perm = (list(range(c)) + ([c, c + 1, c + 2] if (use_xyz or points is None) else [-1, -1, -1]) + [-1] * (ld - c - 3))
+            x, _ = mlp_tc.mlp_chain(img, rows, ld, layers, perm, nsample)
+        else:
+            idx, _, grouped, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32, shift=shift_pred)
+            first = layers[0]
+            if points is not None and not use_xyz:
+                first = dict(first)
+                first["weights"] = torch.cat([first["weights"], torch.zeros((3, first["weights"].shape[1]), device=xyz.device)], dim=0)
+            x = pu._run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
+        outs.append(x.reshape(b, m, x.shape[-1]))
+    return new_xyz, torch.cat(outs, dim=-1), shift_pred, fps_idx

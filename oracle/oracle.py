@@ -255,6 +255,29 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, params):
     return new_points1
 
 
+def multi_encoding_net(xyz, points, fps_idx, radius_list, nsample_list, params_list, shift_pred=None, use_xyz=True):
+    """models/model_rpointnet.py:28-77 with mlp_list2=[], output_shift=False, is_training=False.
+    params_list[i]: layer dicts of radius i ('conv_prev_<i>_<j>' scopes)."""
+    xyz = _f32(xyz)
+    new_xyz = gather_point(xyz, fps_idx)
+    outs = []
+    for radius, nsample, params in zip(radius_list, nsample_list, params_list):
+        idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
+        grouped_xyz = group_point(xyz, idx) - new_xyz[:, :, None, :]
+        if shift_pred is not None:
+            grouped_xyz = grouped_xyz - _f32(shift_pred)[:, :, None, :]
+        if points is not None:
+            g = group_point(points, idx)
+            if use_xyz:
+                g = np.concatenate([g, grouped_xyz], axis=-1)  # points FIRST (:61)
+        else:
+            g = grouped_xyz
+        for layer in params:
+            g = mlp_layer(g, layer)
+        outs.append(g.max(axis=2))
+    return new_xyz, np.concatenate(outs, axis=-1)
+
+
 # ----------------------------------------------------------------------------- oracle/_ref (the reference's own code)
 _ref_cpu = None
 

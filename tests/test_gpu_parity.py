@@ -595,3 +595,25 @@ def test_grid_three_nn_equals_ordered_scan(cuda, oracle, name):
     assert np.array_equal(N(gi), N(si)) and np.array_equal(bits(N(gd)), bits(N(sd)))
     ed, ei = oracle.three_nn(xyz1[:1], xyz2[:1])
     assert np.array_equal(N(gi)[:1], ei) and np.array_equal(bits(N(gd)[:1]), bits(ed))
+
+
+# ------------------------------------------------------------------------------------ multi_encoding_net (config 3)
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_multi_encoding_net_vs_oracle(cuda, oracle, precision, tol):
+    """models/model_rpointnet.py:377 call: 3 radii, nsample 256/256/512 scaled down, mlp [64,128,256], seeds given, shift_pred."""
+    from gspn_b200 import context_encoder
+    rng = np.random.RandomState(9)
+    xyz, col = scenes.scannet_like_batch(70, 2, 8192)
+    fps = oracle.farthest_point_sample(32, xyz)
+    shift = (rng.randn(2, 32, 3) * 0.05).astype(np.float32)
+    radii, ks = [0.5, 1.0, 1.5], [64, 64, 128]
+    params = [rand_layers(rng, 6, [64, 128, 256]) for _ in radii]
+    st = pu.VariableStore(device=cuda)
+    for i, p_ in enumerate(params):
+        st["ctx/conv_prev_%d_" % i] = [{k: T(v, cuda) for k, v in l.items()} for l in p_]
+    nx, feats, _, _ = context_encoder.multi_encoding_net(T(xyz, cuda), T(col, cuda), 32, radii, ks, [[64, 128, 256]] * 3, [], False, None, "ctx",
+                                                         use_xyz=True, shift_pred=T(shift, cuda), fps_idx=T(fps, cuda), variables=st,
+                                                         precision=precision)
+    enx, ef = oracle.multi_encoding_net(xyz, col, fps, radii, ks, params, shift_pred=shift)
+    assert np.array_equal(bits(N(nx)), bits(enx)) and N(feats).shape == (2, 32, 768)
+    assert relerr(N(feats), ef) < tol
