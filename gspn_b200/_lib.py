@@ -40,7 +40,7 @@ SIGNATURES = {
     "gspn_three_nn": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "gspn_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "gspn_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
-    "gspn_nn_distance": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_int, P]),
+    "gspn_nn_distance": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "gspn_nn_distance_grad": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "gspn_mlp_layer_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P]),
     "gspn_max_pool_rows": (c_int, [c_long, c_int, c_int, P, P, P]),

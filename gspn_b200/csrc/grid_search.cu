@@ -288,6 +288,9 @@ __device__ __forceinline__ void insert3(float d, int k, float &b1, float &b2, fl
     }
 }
 
+// TOP1: nn_distance's one-directional 1-NN (tf_nndistance.cpp:21-43) -- the same search keeping only the best; FMA selects
+// the rounding of the compiled NmDistanceKernel instead of the CPU loop's.
+template <bool TOP1, bool FMA>
 __global__ void __launch_bounds__(128) three_nn_grid_kernel(int n, int m, const float *__restrict__ xyz1, const GridHeader *__restrict__ hdr,
                                                             const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                                             float *__restrict__ dist, int *__restrict__ idx, float *__restrict__ weight) {
@@ -316,7 +319,13 @@ __global__ void __launch_bounds__(128) three_nn_grid_kernel(int n, int m, const 
                     const int beg = __ldg(cs + c0), end = __ldg(cs + c0 + (xb - xa) + 1);
                     for (int i = beg; i < end; ++i) {
                         const float4 p = __ldg(sp + i);
-                        insert3(sqdist_nofma(p.x, p.y, p.z, x1, y1, z1), __float_as_int(p.w), b1, b2, b3, i1, i2, i3);
+                        const float d = FMA ? sqdist_fma(p.x, p.y, p.z, x1, y1, z1) : sqdist_nofma(p.x, p.y, p.z, x1, y1, z1);
+                        const int k = __float_as_int(p.w);
+                        if (TOP1) {
+                            if (d < b1 || (d == b1 && k < i1)) { b1 = d; i1 = k; }
+                        } else {
+                            insert3(d, k, b1, b2, b3, i1, i2, i3);
+                        }
                     }
                 }
         }
@@ -324,7 +333,12 @@ __global__ void __launch_bounds__(128) three_nn_grid_kernel(int n, int m, const 
         // every unvisited point is farther than R*h from the query along some axis; accept only with a safety margin
         // far above float rounding (1e-3 relative on the radius), so no unvisited point can tie or beat b3
         const float cover = (float)R * g.h * 0.999f;
-        if (b3 < cover * cover) break;
+        if ((TOP1 ? b1 : b3) < cover * cover) break;
+    }
+    if (TOP1) {
+        dist[(size_t)cloud * n + j] = b1;
+        idx[(size_t)cloud * n + j] = i1;
+        return;
     }
     const size_t o = ((size_t)cloud * n + j) * 3;
     dist[o] = b1; dist[o + 1] = b2; dist[o + 2] = b3;
@@ -381,6 +395,19 @@ int gspn_three_nn_grid_launch(int b, int n, int m, const float *xyz1, const floa
     int rc = build_grid(b, m, xyz2, 0.f, target, ws, s);
     if (rc != GSPN_OK) return rc;
     dim3 grid(ceil_div(n, 128), b);
-    three_nn_grid_kernel<<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, weight);
+    three_nn_grid_kernel<false, false><<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, weight);
+    return check_launch();
+}
+
+// one direction of nn_distance through the grid (grid over xyz2, queries xyz1)
+int gspn_nn_one_way_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, int fma, void *workspace,
+                                cudaStream_t s) {
+    GridWs ws = carve(workspace, b, m);
+    float target = (float)m < (float)kGridMaxCells ? (float)m : (float)kGridMaxCells;
+    int rc = build_grid(b, m, xyz2, 0.f, target, ws, s);
+    if (rc != GSPN_OK) return rc;
+    dim3 grid(ceil_div(n, 128), b);
+    if (fma) three_nn_grid_kernel<true, true><<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, nullptr);
+    else three_nn_grid_kernel<true, false><<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, nullptr);
     return check_launch();
 }

@@ -148,6 +148,8 @@ using namespace gspn;
 // grid_search.cu
 int gspn_three_nn_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight, void *workspace,
                               cudaStream_t s);
+int gspn_nn_one_way_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, int fma, void *workspace,
+                                cudaStream_t s);
 extern "C" size_t gspn_grid_workspace_bytes(int b, int n);
 
 extern "C" int gspn_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight,
@@ -171,12 +173,18 @@ extern "C" int gspn_three_nn(int b, int n, int m, const float *xyz1, const float
 }
 
 extern "C" int gspn_nn_distance(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist1, int *idx1, float *dist2, int *idx2,
-                                int rounding, gspn_stream_t stream) {
+                                int rounding, void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
     GSPN_REQUIRE(b >= 0 && n > 0 && m > 0 && b <= 65535);  // tf_nndistance.cpp:51-58
     GSPN_REQUIRE(rounding == 0 || rounding == 1);
     if (b == 0) return GSPN_OK;
     GSPN_REQUIRE_PTR(xyz1); GSPN_REQUIRE_PTR(xyz2); GSPN_REQUIRE_PTR(dist1); GSPN_REQUIRE_PTR(idx1); GSPN_REQUIRE_PTR(dist2); GSPN_REQUIRE_PTR(idx2);
     cudaStream_t s = as_stream(stream);
+    if (workspace != nullptr && n >= 2048 && m >= 2048) {  // both directions through a grid over the scanned set
+        if (workspace_bytes < gspn_grid_workspace_bytes(b, n > m ? n : m)) return GSPN_E_WORKSPACE;
+        int rc = gspn_nn_one_way_grid_launch(b, n, m, xyz1, xyz2, dist1, idx1, rounding, workspace, s);
+        if (rc != GSPN_OK) return rc;
+        return gspn_nn_one_way_grid_launch(b, m, n, xyz2, xyz1, dist2, idx2, rounding, workspace, s);
+    }
     if (rounding) {
         launch_nn<true>(b, n, m, xyz1, xyz2, dist1, idx1, s);
         launch_nn<true>(b, m, n, xyz2, xyz1, dist2, idx2, s);

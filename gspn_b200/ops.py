@@ -212,7 +212,9 @@ class _NnDistance(torch.autograd.Function):
         i1 = torch.empty((b, n), dtype=torch.int32, device=dev)
         d2 = torch.empty((b, m), dtype=torch.float32, device=dev)
         i2 = torch.empty((b, m), dtype=torch.int32, device=dev)
-        check(_lib.lib().gspn_nn_distance(b, n, m, _p(xyz1), _p(xyz2), _p(d1), _p(i1), _p(d2), _p(i2), rounding, _stream()), "nn_distance")
+        ws, wsb = _grid_ws(b, max(n, m), dev, 2048) if min(n, m) >= 2048 else (None, 0)
+        check(_lib.lib().gspn_nn_distance(b, n, m, _p(xyz1), _p(xyz2), _p(d1), _p(i1), _p(d2), _p(i2), rounding, _p(ws), wsb, _stream()),
+              "nn_distance")
         ctx.save_for_backward(xyz1, xyz2, i1, i2)
         ctx.mark_non_differentiable(i1, i2)
         return d1, i1, d2, i2

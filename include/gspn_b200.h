@@ -137,9 +137,12 @@ int gspn_three_interpolate_grad(int b, int n, int c, int m, const float *grad_ou
  *   nnsearch tf_nndistance.cpp:21-43 (CPU op) / NmDistanceKernelLauncher tf_nndistance_g.cu:128 (GPU op)
  * xyz1 (b,n,3), xyz2 (b,m,3) -> dist1 (b,n), idx1 (b,n), dist2 (b,m), idx2 (b,m).
  * rounding: 0 = as the CPU op rounds (mul,mul,add,mul,add), 1 = as the compiled
- * GPU kernel rounds (mul,fma,fma).  Ties -> lowest index in both. */
+ * GPU kernel rounds (mul,fma,fma).  Ties -> lowest index in both.
+ * workspace (optional): gspn_grid_workspace_bytes(b, max(n,m)); with it and n,m >= 2048 both directions search a
+ * uniform grid over the scanned set instead of the O(n*m) scan -- identical results. */
 int gspn_nn_distance(int b, int n, int m, const float *xyz1, const float *xyz2,
-                     float *dist1, int *idx1, float *dist2, int *idx2, int rounding, gspn_stream_t stream);
+                     float *dist1, int *idx1, float *dist2, int *idx2, int rounding,
+                     void *workspace, size_t workspace_bytes, gspn_stream_t stream);
 /* NnDistanceGrad  tf_nndistance.py:31-37; tf_nndistance.cpp:126-163 / tf_nndistance_g.cu:152 */
 int gspn_nn_distance_grad(int b, int n, int m, const float *xyz1, const float *xyz2,
                           const float *grad_dist1, const int *idx1, const float *grad_dist2, const int *idx2,

@@ -46,7 +46,7 @@ def test_argument_checks_need_no_gpu():
     assert L.gspn_farthest_point_sample(1, 8, 4, None, None, None, 0, None) == _lib.GSPN_E_NULL_PTR
     assert L.gspn_query_ball_point(1, 8, 4, -1.0, 4, None, None, None, None, None, 0, None) == _lib.GSPN_E_BAD_SHAPE
     assert L.gspn_query_ball_point(1, 8, 4, 0.5, 0, None, None, None, None, None, 0, None) == _lib.GSPN_E_BAD_SHAPE
-    assert L.gspn_nn_distance(1, 8, 8, None, None, None, None, None, None, 7, None) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_nn_distance(1, 8, 8, None, None, None, None, None, None, 7, None, 0, None) == _lib.GSPN_E_BAD_SHAPE
     assert L.gspn_grouped_bytes(256, 6, _lib.GSPN_DT_BF16) == 2 * 16384
     assert L.gspn_grouped_bytes(129, 67, _lib.GSPN_DT_BF16) == 2 * 2 * 16384
 

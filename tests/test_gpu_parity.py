@@ -617,3 +617,26 @@ def test_multi_encoding_net_vs_oracle(cuda, oracle, precision, tol):
     enx, ef = oracle.multi_encoding_net(xyz, col, fps, radii, ks, params, shift_pred=shift)
     assert np.array_equal(bits(N(nx)), bits(enx)) and N(feats).shape == (2, 32, 768)
     assert relerr(N(feats), ef) < tol
+
+
+@pytest.mark.parametrize("kind", ["randn", "scene_dups"])
+def test_grid_nn_distance_equals_ordered_scan(cuda, oracle, kind):
+    rng = np.random.RandomState(3)
+    if kind == "randn":  # tf_nndistance.py:48-49 demo distribution
+        a = rng.randn(2, 9000, 3).astype(np.float32)
+        c = rng.randn(2, 5000, 3).astype(np.float32)
+    else:
+        a = scenes.with_duplicates(scenes.scannet_like_batch(80, 2, 9000)[0], 0.3)
+        c = scenes.scannet_like_batch(81, 2, 5000)[0]
+        c[:, :1000] = a[:, :1000]
+    for rounding, variant in (("cpu", False), ("gpu", True)):
+        got = [N(t) for t in gspn_b200.nn_distance(T(a, cuda), T(c, cuda), rounding=rounding)]
+        ops.GRID_SEARCH = False
+        try:
+            scan = [N(t) for t in gspn_b200.nn_distance(T(a, cuda), T(c, cuda), rounding=rounding)]
+        finally:
+            ops.GRID_SEARCH = True
+        exp = oracle.nn_distance(a[:1], c[:1], gpu_variant=variant)
+        for g, s_, e in zip(got, scan, exp):
+            assert np.array_equal(bits(g), bits(s_)), rounding
+            assert np.array_equal(bits(g[:1]), bits(e)), rounding
