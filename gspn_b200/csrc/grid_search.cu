@@ -22,7 +22,9 @@
 
 namespace gspn {
 
-constexpr int kGridMaxCells = 32768;
+constexpr int kGridMinCap = 32768;
+// cell budget per cloud: about two cells per scanned point, between 32 Ki and 1 Mi
+static inline int grid_cap(int n) { long c = 2L * n; c = c < kGridMinCap ? kGridMinCap : c; c = c > (1L << 20) ? (1L << 20) : c; return (int)c; }
 constexpr int kHitCap = 512;  // per-warp hit buffer (indices) of the grid ball query
 constexpr int kGQWarps = 8;
 
@@ -32,7 +34,7 @@ struct __align__(16) GridHeader {
     int pad[3];
 };
 
-// workspace: [GridHeader x b][cell_start (kGridMaxCells+1) x b][cursor kGridMaxCells x b][sorted float4 n x b]
+// workspace: [GridHeader x b][sorted float4 n x b][cell_start (cap+4) x b][cursor (cap+4) x b], cap = grid_cap(n)
 struct GridWs {
     GridHeader *hdr;
     int *cell_start;
@@ -40,14 +42,14 @@ struct GridWs {
     float4 *sorted;
 };
 static size_t grid_ws_bytes(int b, int n) {
-    return (size_t)b * (sizeof(GridHeader) + sizeof(int) * 2 * ((size_t)kGridMaxCells + 4) + sizeof(float4) * (size_t)n) + 256;
+    return (size_t)b * (sizeof(GridHeader) + sizeof(int) * 2 * ((size_t)grid_cap(n) + 4) + sizeof(float4) * (size_t)n) + 256;
 }
 static GridWs carve(void *ws, int b, int n) {
     GridWs g;
     unsigned char *p = (unsigned char *)(((uintptr_t)ws + 127) & ~(uintptr_t)127);
     g.hdr = (GridHeader *)p; p += (size_t)b * sizeof(GridHeader);
     g.sorted = (float4 *)p; p += (size_t)b * n * sizeof(float4);
-    g.cell_start = (int *)p; p += (size_t)b * (kGridMaxCells + 4) * sizeof(int);
+    g.cell_start = (int *)p; p += (size_t)b * (grid_cap(n) + 4) * sizeof(int);
     g.cursor = (int *)p;
     return g;
 }
@@ -60,7 +62,7 @@ __device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int g) 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ---- 1. bounding box + grid geometry, one CTA per cloud
-__global__ void __launch_bounds__(1024) grid_bbox_kernel(int n, const float *__restrict__ xyz, float h_min, float target_cells, GridHeader *hdr) {
+__global__ void __launch_bounds__(1024) grid_bbox_kernel(int n, const float *__restrict__ xyz, float h_min, float target_cells, int cap, GridHeader *hdr) {
     __shared__ float red[6][32];
     const int cloud = blockIdx.x;
     const float *p = xyz + (size_t)cloud * n * 3;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(1024) grid_bbox_kernel(int n, const float *__r
         int gx, gy, gz;
         for (;;) {
             gx = (int)(ex / h) + 1; gy = (int)(ey / h) + 1; gz = (int)(ez / h) + 1;
-            if ((long)gx * gy * gz <= kGridMaxCells) break;
+            if ((long)gx * gy * gz <= cap) break;
             h *= 1.26f;
         }
         GridHeader g;
@@ -115,21 +117,21 @@ __device__ __forceinline__ int point_cell(const GridHeader &g, float x, float y,
 }
 
 // ---- 2. histogram of points per cell (counts pre-zeroed)
-__global__ void __launch_bounds__(256) grid_count_kernel(int n, const float *__restrict__ xyz, const GridHeader *__restrict__ hdr, int *counts) {
+__global__ void __launch_bounds__(256) grid_count_kernel(int n, int cap, const float *__restrict__ xyz, const GridHeader *__restrict__ hdr, int *counts) {
     const int cloud = blockIdx.y;
     const GridHeader g = hdr[cloud];
     const float *p = xyz + (size_t)cloud * n * 3;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-        atomicAdd(counts + (size_t)cloud * (kGridMaxCells + 4) + point_cell(g, __ldg(p + 3 * k), __ldg(p + 3 * k + 1), __ldg(p + 3 * k + 2)), 1);
+        atomicAdd(counts + (size_t)cloud * (cap + 4) + point_cell(g, __ldg(p + 3 * k), __ldg(p + 3 * k + 1), __ldg(p + 3 * k + 2)), 1);
 }
 
 // ---- 3. exclusive scan of the counts in place (cell_start) + copy to the scatter cursors, one CTA per cloud
-__global__ void __launch_bounds__(1024) grid_scan_kernel(const GridHeader *__restrict__ hdr, int *cell_start, int *cursor) {
+__global__ void __launch_bounds__(1024) grid_scan_kernel(int cap, const GridHeader *__restrict__ hdr, int *cell_start, int *cursor) {
     __shared__ int wsum[32];
     const int cloud = blockIdx.x;
     const int ncells = hdr[cloud].ncells;
-    int *cs = cell_start + (size_t)cloud * (kGridMaxCells + 4);
-    int *cu = cursor + (size_t)cloud * (kGridMaxCells + 4);
+    int *cs = cell_start + (size_t)cloud * (cap + 4);
+    int *cu = cursor + (size_t)cloud * (cap + 4);
     const int per = (ncells + blockDim.x - 1) / blockDim.x;
     const int c0 = threadIdx.x * per, c1 = min(c0 + per, ncells);
     int sum = 0;
@@ -164,30 +166,31 @@ __global__ void __launch_bounds__(1024) grid_scan_kernel(const GridHeader *__res
 }
 
 // ---- 4. scatter points into cell order as (x,y,z,index)
-__global__ void __launch_bounds__(256) grid_scatter_kernel(int n, const float *__restrict__ xyz, const GridHeader *__restrict__ hdr, int *cursor,
+__global__ void __launch_bounds__(256) grid_scatter_kernel(int n, int cap, const float *__restrict__ xyz, const GridHeader *__restrict__ hdr, int *cursor,
                                                            float4 *sorted) {
     const int cloud = blockIdx.y;
     const GridHeader g = hdr[cloud];
     const float *p = xyz + (size_t)cloud * n * 3;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1), z = __ldg(p + 3 * k + 2);
-        int pos = atomicAdd(cursor + (size_t)cloud * (kGridMaxCells + 4) + point_cell(g, x, y, z), 1);
+        int pos = atomicAdd(cursor + (size_t)cloud * (cap + 4) + point_cell(g, x, y, z), 1);
         sorted[(size_t)cloud * n + pos] = make_float4(x, y, z, __int_as_float(k));
     }
 }
 
 static int build_grid(int b, int n, const float *xyz, float h_min, float target_cells, const GridWs &ws, cudaStream_t s) {
-    GSPN_CUDA_OK(cudaMemsetAsync(ws.cell_start, 0, sizeof(int) * (size_t)b * (kGridMaxCells + 4), s));
-    grid_bbox_kernel<<<b, 1024, 0, s>>>(n, xyz, h_min, target_cells, ws.hdr);
+    const int cap = grid_cap(n);
+    GSPN_CUDA_OK(cudaMemsetAsync(ws.cell_start, 0, sizeof(int) * (size_t)b * (cap + 4), s));
+    grid_bbox_kernel<<<b, 1024, 0, s>>>(n, xyz, h_min, target_cells < (float)cap ? target_cells : (float)cap, cap, ws.hdr);
     dim3 grid(ceil_div(n, 256) < 64 ? ceil_div(n, 256) : 64, b);
-    grid_count_kernel<<<grid, 256, 0, s>>>(n, xyz, ws.hdr, ws.cell_start);
-    grid_scan_kernel<<<b, 1024, 0, s>>>(ws.hdr, ws.cell_start, ws.cursor);
-    grid_scatter_kernel<<<grid, 256, 0, s>>>(n, xyz, ws.hdr, ws.cursor, ws.sorted);
+    grid_count_kernel<<<grid, 256, 0, s>>>(n, cap, xyz, ws.hdr, ws.cell_start);
+    grid_scan_kernel<<<b, 1024, 0, s>>>(cap, ws.hdr, ws.cell_start, ws.cursor);
+    grid_scatter_kernel<<<grid, 256, 0, s>>>(n, cap, xyz, ws.hdr, ws.cursor, ws.sorted);
     return check_launch();
 }
 
 // ---- ball query through the grid: one warp per query
-__global__ void __launch_bounds__(kGQWarps * 32) ballquery_grid_kernel(int n, int m, float s_max, int nsample, const float *__restrict__ xyz1,
+__global__ void __launch_bounds__(kGQWarps * 32) ballquery_grid_kernel(int n, int m, int cap, float s_max, int nsample, const float *__restrict__ xyz1,
                                                                        const float *__restrict__ xyz2, const GridHeader *__restrict__ hdr,
                                                                        const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                                                        int *__restrict__ idx, int *__restrict__ pts_cnt, GroupArgs ga) {
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kGQWarps * 32) ballquery_grid_kernel(int n, in
     int *hits = smem_i + warp * kHitCap;
     int *row = smem_i + kGQWarps * kHitCap + warp * nsample;
     const GridHeader g = hdr[cloud];
-    const int *cs = cell_start + (size_t)cloud * (kGridMaxCells + 4);
+    const int *cs = cell_start + (size_t)cloud * (cap + 4);
     const float4 *sp = sorted + (size_t)cloud * n;
     const float *q = xyz2 + ((size_t)cloud * m + j) * 3;
     const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
@@ -291,14 +294,14 @@ __device__ __forceinline__ void insert3(float d, int k, float &b1, float &b2, fl
 // TOP1: nn_distance's one-directional 1-NN (tf_nndistance.cpp:21-43) -- the same search keeping only the best; FMA selects
 // the rounding of the compiled NmDistanceKernel instead of the CPU loop's.
 template <bool TOP1, bool FMA>
-__global__ void __launch_bounds__(128) three_nn_grid_kernel(int n, int m, const float *__restrict__ xyz1, const GridHeader *__restrict__ hdr,
+__global__ void __launch_bounds__(128) three_nn_grid_kernel(int n, int m, int cap, const float *__restrict__ xyz1, const GridHeader *__restrict__ hdr,
                                                             const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                                             float *__restrict__ dist, int *__restrict__ idx, float *__restrict__ weight) {
     const int cloud = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const GridHeader g = hdr[cloud];
-    const int *cs = cell_start + (size_t)cloud * (kGridMaxCells + 4);
+    const int *cs = cell_start + (size_t)cloud * (cap + 4);
     const float4 *sp = sorted + (size_t)cloud * m;
     const float *u = xyz1 + ((size_t)cloud * n + j) * 3;
     const float x1 = __ldg(u), y1 = __ldg(u + 1), z1 = __ldg(u + 2);
@@ -382,7 +385,7 @@ int gspn_ballquery_grid_launch(int b, int n, int m, float radius, int nsample, c
     if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;
     if (smem > 48 * 1024) GSPN_CUDA_OK(cudaFuncSetAttribute(ballquery_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(m, kGQWarps), b);
-    ballquery_grid_kernel<<<grid, kGQWarps * 32, smem, s>>>(n, m, grid_ball_threshold(radius), nsample, xyz1, xyz2, ws.hdr, ws.cell_start,
+    ballquery_grid_kernel<<<grid, kGQWarps * 32, smem, s>>>(n, m, grid_cap(n), grid_ball_threshold(radius), nsample, xyz1, xyz2, ws.hdr, ws.cell_start,
                                                            ws.sorted, idx, pts_cnt, ga);
     return check_launch();
 }
@@ -391,11 +394,11 @@ int gspn_three_nn_grid_launch(int b, int n, int m, const float *xyz1, const floa
                               cudaStream_t s) {
     GridWs ws = carve(workspace, b, m);
     // about one known point per cell: the 3x3x3 block then holds the three nearest for almost every query
-    float target = (float)m < (float)kGridMaxCells ? (float)m : (float)kGridMaxCells;
+    float target = (float)m;
     int rc = build_grid(b, m, xyz2, 0.f, target, ws, s);
     if (rc != GSPN_OK) return rc;
     dim3 grid(ceil_div(n, 128), b);
-    three_nn_grid_kernel<false, false><<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, weight);
+    three_nn_grid_kernel<false, false><<<grid, 128, 0, s>>>(n, m, grid_cap(m), xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, weight);
     return check_launch();
 }
 
@@ -403,11 +406,11 @@ int gspn_three_nn_grid_launch(int b, int n, int m, const float *xyz1, const floa
 int gspn_nn_one_way_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, int fma, void *workspace,
                                 cudaStream_t s) {
     GridWs ws = carve(workspace, b, m);
-    float target = (float)m < (float)kGridMaxCells ? (float)m : (float)kGridMaxCells;
+    float target = (float)m;
     int rc = build_grid(b, m, xyz2, 0.f, target, ws, s);
     if (rc != GSPN_OK) return rc;
     dim3 grid(ceil_div(n, 128), b);
-    if (fma) three_nn_grid_kernel<true, true><<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, nullptr);
-    else three_nn_grid_kernel<true, false><<<grid, 128, 0, s>>>(n, m, xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, nullptr);
+    if (fma) three_nn_grid_kernel<true, true><<<grid, 128, 0, s>>>(n, m, grid_cap(m), xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, nullptr);
+    else three_nn_grid_kernel<true, false><<<grid, 128, 0, s>>>(n, m, grid_cap(m), xyz1, ws.hdr, ws.cell_start, ws.sorted, dist, idx, nullptr);
     return check_launch();
 }
