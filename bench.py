@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--scenes-per-gpu", type=int, default=SCENES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=3, help="batches kept in flight (CUDA-graph lanes on separate streams)")
+    ap.add_argument("--depth", type=int, default=6, help="batches kept in flight (CUDA-graph lanes on separate streams)")
     ap.add_argument("--no-graphs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -17,6 +17,8 @@
 // (:130,:146) + left-wins tree (:158).  The key  ((k&511)<<23)|(k>>9)  orders exactly like that,
 // independent of how points are mapped to threads here.
 #include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -399,6 +401,12 @@ extern "C" int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *
     GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out);
     int t0, p0, c0;
     choose_cfg(n, &t0, &p0, &c0);
+    if (n > 16384) {  // tuning door for the large-cloud mapping: GSPN_FPS_CFG="threads,ppt,cluster"
+        if (const char *e = getenv("GSPN_FPS_CFG")) {
+            int a = 0, b2 = 0, c2 = 0;
+            if (sscanf(e, "%d,%d,%d", &a, &b2, &c2) == 3 && (long)a * b2 * c2 >= n) { t0 = a; p0 = b2; c0 = c2; }
+        }
+    }
     if (threads <= 0) threads = t0;
     if (ppt <= 0) ppt = p0;
     if (cluster <= 0) cluster = c0;
