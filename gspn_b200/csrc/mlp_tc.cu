@@ -21,8 +21,8 @@
 namespace gspn {
 
 constexpr int kMaxLayers = 4;
-constexpr int kMaxEpiWarps = 8;  // 4 or 8 epilogue warps (thread 0 also issues the MMAs) + 2 producer warps
-constexpr int kMaxTcThreads = kMaxEpiWarps * 32 + 64;
+constexpr int kMaxEpiWarps = 8;  // 4 or 8 epilogue warps + input producer + weight producer + MMA issuer (one lane each)
+constexpr int kMaxTcThreads = kMaxEpiWarps * 32 + 96;
 constexpr int kMaxStages = 4;
 
 struct ChainParams {
@@ -124,10 +124,11 @@ struct Cursor {  // position in the per-tile weight block sequence: layer, k-blo
     }
 };
 
-__global__ void __launch_bounds__(kMaxTcThreads) mlp_chain_kernel(const ChainParams p) {
+template <int EPI>  // epilogue warps: 4 (two CTAs per SM) or 8 (one CTA per SM)
+__global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_kernel(const ChainParams p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 1];
+    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t raw = s_u32(smem_raw);
@@ -142,10 +143,12 @@ __global__ void __launch_bounds__(kMaxTcThreads) mlp_chain_kernel(const ChainPar
                                              (size_t)p.w_stages * p.stage_bytes);  // [4 warps][32][33] output transpose pad
     float *affine = xpose + (p.pool == 1 ? p.epi_warps * 32 * 33 : 0);  // 32*33*4 bytes per pad keeps 16-byte alignment
     const uint32_t w_full = s_u32(&bars[0]), w_empty = s_u32(&bars[kMaxStages]), a_full = s_u32(&bars[2 * kMaxStages]),
-                   a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]);
+                   a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]),
+                   epi_done = s_u32(&bars[4 * kMaxStages + 1]);
 
     if (tid == 0) {
         for (int i = 0; i < 4 * kMaxStages + 1; ++i) mb_init(s_u32(&bars[i]), 1);
+        mb_init(epi_done, p.epi_warps * 32);  // every epilogue thread arrives once per layer-step
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
@@ -212,50 +215,63 @@ __global__ void __launch_bounds__(kMaxTcThreads) mlp_chain_kernel(const ChainPar
                 if (++s == p.w_stages) { s = 0; par ^= 1; }
             }
         }
+    } else if (warp == p.epi_warps + 2) {
+        // ---- MMA issuer: one lane.  Operand waits and descriptor arithmetic run ahead of the epilogue warps; the only
+        // thing on the layer-to-layer critical path is  wait(epi_done) -> tcgen05.mma ... -> commit(mma_done)
+        if (lane == 0) {
+            int wu_s = 0, wu_par = 0, au_s = 0, au_par = 0;  // consumer-side stage index and round parity
+            uint32_t epi_par = 0;
+            bool first = true;
+            for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                for (int l = 0; l < p.nlayers; ++l) {
+                    const int Nl = p.N[l], KBl = p.K[l] >> 6;
+                    const int nchunks = (Nl + p.nch - 1) / p.nch;
+                    // operands of the first block first (usually long landed), then the previous epilogue
+                    if (l == 0) mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
+                    mb_wait(w_full + 8 * wu_s, (uint32_t)wu_par);
+                    if (!first) { mb_wait(epi_done, epi_par); epi_par ^= 1; }  // TMEM drained, next A operand written
+                    first = false;
+                    tc_fence_after();
+                    for (int kb = 0; kb < KBl; ++kb) {
+                        uint32_t a_addr;
+                        if (l == 0) {
+                            if (kb) mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
+                            a_addr = aring + au_s * kTileBytes;
+                        } else {
+                            a_addr = R[(l - 1) & 1] + kb * kTileBytes;
+                        }
+                        const uint64_t ad = smem_desc(a_addr);
+                        for (int nc = 0; nc < nchunks; ++nc) {
+                            const int s = wu_s;
+                            if (kb | nc) mb_wait(w_full + 8 * s, (uint32_t)wu_par);
+                            tc_fence_after();
+                            const int nrows = min(p.nch, Nl - nc * p.nch);
+                            const uint32_t idesc = instr_desc(128, nrows);
+                            const uint64_t bd = smem_desc(wring + s * p.stage_bytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
+                                tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                            tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
+                            if (++wu_s == p.w_stages) { wu_s = 0; wu_par ^= 1; }
+                        }
+                        if (l == 0) {
+                            tc_commit(a_empty + 8 * au_s);
+                            if (++au_s == p.a_stages) { au_s = 0; au_par ^= 1; }
+                        }
+                    }
+                    tc_commit(mma_done);
+                }
+            }
+        }
     } else {
-    // ---- MMA issue (thread 0) + epilogue (warps 0-3)
-    int wu_s = 0, wu_par = 0, au_s = 0, au_par = 0;  // consumer-side stage index and round parity
+    // ---- epilogue warps
     uint32_t done_par = 0;
 
     for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         for (int l = 0; l < p.nlayers; ++l) {
-            const int Nl = p.N[l], KBl = p.K[l] >> 6;
+            const int Nl = p.N[l];
             long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
-            if (p.prof) pt0 = clock64();
-            if (tid == 0) {
-                tc_fence_after();
-                const int nchunks = (Nl + p.nch - 1) / p.nch;
-                for (int kb = 0; kb < KBl; ++kb) {
-                    uint32_t a_addr;
-                    if (l == 0) {
-                        mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
-                        a_addr = aring + au_s * kTileBytes;
-                    } else {
-                        a_addr = R[(l - 1) & 1] + kb * kTileBytes;
-                    }
-                    const uint64_t ad = smem_desc(a_addr);
-                    for (int nc = 0; nc < nchunks; ++nc) {
-                        const int s = wu_s;
-                        mb_wait(w_full + 8 * s, (uint32_t)wu_par);
-                        tc_fence_after();
-                        const int nrows = min(p.nch, Nl - nc * p.nch);
-                        const uint32_t idesc = instr_desc(128, nrows);
-                        const uint64_t bd = smem_desc(wring + s * p.stage_bytes);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
-                            tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-                        tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
-                        if (++wu_s == p.w_stages) { wu_s = 0; wu_par ^= 1; }
-                    }
-                    if (l == 0) {
-                        tc_commit(a_empty + 8 * au_s);
-                        if (++au_s == p.a_stages) { au_s = 0; au_par ^= 1; }
-                    }
-                }
-                tc_commit(mma_done);
-            }
-            __syncwarp();
-            if (p.prof) pt1 = clock64();
+            if (p.prof) pt0 = pt1 = clock64();
             mb_wait(mma_done, done_par);
             done_par ^= 1;
             tc_fence_after();
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(kMaxTcThreads) mlp_chain_kernel(const ChainPar
             if (p.prof) pt3 = clock64();
             tc_fence_before();
             fence_proxy_async();  // epilogue st.shared -> visible to the tensor core's async-proxy reads
-            asm volatile("bar.sync 1, %0;" ::"r"(p.epi_warps * 32) : "memory");  // the epilogue warps only; producers run free
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done) : "memory");  // hand the tile back to the MMA issuer
             if (p.prof && blockIdx.x == 0 && tid == 0) {
                 long long pt4 = clock64();
                 atomicAdd((unsigned long long *)p.prof + 0, (unsigned long long)(pt1 - pt0));  // issue (loads + MMAs)
@@ -527,7 +543,7 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
         if (sz > 226 * 1024) continue;
         int o = (int)((228 * 1024) / (sz + 1024));
         o = o > occ_tmem ? occ_tmem : o;
-        o = o > 2 ? 2 : o;  // 168 registers x 192 threads: two CTAs fill the register file
+        o = o > 2 ? 2 : o;  // ~160 registers x 224 threads: two CTAs fill the register file
         if (o > occ) { occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1]; }
     }
     if (occ < 1) return GSPN_E_UNSUPPORTED;
@@ -538,7 +554,8 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     static int smem_attr_set = 0;  // launch attribute already raised to at least this (benign race: set is idempotent)
     if ((int)smem > smem_attr_set) {
         // 227 KiB is the per-CTA limit for static + dynamic together; leave 1 KiB for the kernel's static __shared__
-        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         smem_attr_set = 226 * 1024;
     }
     static int sms_cached = 0;
@@ -554,7 +571,8 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
     // one CTA per SM (shared-memory bound): give it 8 epilogue warps; two CTAs per SM: 4 each (register file)
     p.epi_warps = occ >= 2 ? 4 : 8;
-    mlp_chain_kernel<<<(unsigned)grid, p.epi_warps * 32 + 64, smem, s>>>(p);
+    if (p.epi_warps == 4) mlp_chain_kernel<4><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p);
+    else mlp_chain_kernel<8><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p);
     return check_launch();
 }
 
