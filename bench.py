@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--depth", type=int, default=6, help="batches kept in flight (CUDA-graph lanes on separate streams)")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg downloads the fp32 copy of the feature map (PCIe-bound)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -287,7 +288,9 @@ def main():
     torch.cuda.synchronize(); barrier()
     ms = t_start.elapsed_time(t_end) / args.steps
     # ---- e2e: pinned host in, per-point features out, copies inside the timed region
-    out_host = [torch.empty((B, NPOINTS, backbone.FP_SPECS[-1][-1]), dtype=torch.float32).pin_memory() for _ in range(args.depth)]
+    # the result read back every step is the per-point feature map in the precision the path computes in
+    out_dtype = torch.bfloat16 if (precision == "bf16" and not args.e2e_fp32) else torch.float32
+    out_host = [torch.empty((B, NPOINTS, backbone.FP_SPECS[-1][-1]), dtype=out_dtype).pin_memory() for _ in range(args.depth)]
     for w in range(2 * args.depth):
         eng.result_to_host(eng.submit(host_xyz[w % ROTATE], host_col[w % ROTATE]), out_host[w % args.depth])
     eng.synchronize()
@@ -347,7 +350,7 @@ def main():
                             "reported because the contract asks for it, see DESIGN.md; per-stage rooflines in 'kernels'"}
     total_points = world * B * NPOINTS
     h2d = B * NPOINTS * 6 * 4
-    d2h = out_host[0].numel() * 4
+    d2h = out_host[0].numel() * out_host[0].element_size()
     line = {
         "metric": "SA+FP points/sec on 32768-pt scenes", "value": total_points / (ms * 1e-3), "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -358,7 +361,7 @@ def main():
                    else "%d eager streams" % args.depth,
                    "l2": "rotating %d distinct input batches; per-step intermediates (>300 MB) exceed the 126 MB L2" % ROTATE},
         "e2e": {"value": total_points / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h},
+                "d2h_bytes_per_step": d2h, "result": "l0_points (b,n,128) %s to pinned host" % str(out_dtype).replace("torch.", "")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -54,7 +54,7 @@ def random_variables(device, colour_channels=3, seed=7, bn_seed=8, sa_specs=SA_S
     return store, as_numpy
 
 
-def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=None, timers=None):
+def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=None, timers=None, l0_bf16=False):
     """xyz (b,n,3), colour (b,n,c) CUDA f32 -> dict(l0_points (b,n,128), l1..l4 xyz/points, indices).
     timers: optional callable(name) -> context manager, used by bench.py to bracket stages with CUDA events."""
     def stage(name):
@@ -70,10 +70,16 @@ def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=
     up = ps[4]
     for i, mlp in enumerate(fp_specs):
         lvl = 3 - i
+        want_h = l0_bf16 and i == len(fp_specs) - 1 and (precision or pu.DEFAULT_PRECISION) == "bf16"
         with stage("fp%d" % (i + 1)):
             up = pu.pointnet_fp_module(xs[lvl], xs[lvl + 1], ps[lvl], up, mlp, False, None, "fa_layer%d" % (i + 1), variables=store,
-                                       precision=precision, timers=timers)
-    return {"l0_points": up, "xyz": xs, "points": ps, "idx": idxs}
+                                       precision=precision, timers=timers, also_bf16=want_h)
+    out = {"xyz": xs, "points": ps, "idx": idxs}
+    if isinstance(up, tuple):
+        out["l0_points"], out["l0_points_bf16"] = up
+    else:
+        out["l0_points"] = up
+    return out
 
 
 class _Null:

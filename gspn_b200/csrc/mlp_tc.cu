@@ -21,8 +21,6 @@
 namespace gspn {
 
 constexpr int kMaxLayers = 4;
-constexpr int kMaxEpiWarps = 8;  // 4 or 8 epilogue warps + input producer + weight producer + MMA issuer (one lane each)
-constexpr int kMaxTcThreads = kMaxEpiWarps * 32 + 96;
 constexpr int kMaxStages = 4;
 
 struct ChainParams {
@@ -106,6 +104,12 @@ __device__ __forceinline__ uint32_t instr_desc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -130,7 +134,10 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the
+    // MMA issuer's operands can live in uniform registers (no per-instruction R2UR waterfall)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(GSPN_FULL_MASK, tid >> 5, 0);
     const uint32_t raw = s_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
     unsigned char *sm = smem_raw + (base - raw);
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
 
     if (tid == 0) {
         for (int i = 0; i < 4 * kMaxStages + 1; ++i) mb_init(s_u32(&bars[i]), 1);
-        mb_init(epi_done, p.epi_warps * 32);  // every epilogue thread arrives once per layer-step
+        mb_init(epi_done, p.epi_warps);  // one elected lane per epilogue warp arrives once per layer-step
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
@@ -216,50 +223,74 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             }
         }
     } else if (warp == p.epi_warps + 2) {
-        // ---- MMA issuer: one lane.  Operand waits and descriptor arithmetic run ahead of the epilogue warps; the only
-        // thing on the layer-to-layer critical path is  wait(epi_done) -> tcgen05.mma ... -> commit(mma_done)
-        if (lane == 0) {
+        // ---- MMA issuer warp.  The whole warp runs the loop CONVERGED (barrier waits, ring bookkeeping and descriptor
+        // arithmetic stay warp-uniform, so they live in uniform registers next to the UTCHMMA operands); only the
+        // tcgen05.mma / tcgen05.commit instructions themselves are executed by one lane.  Operand waits run ahead of the
+        // epilogue warps; the layer-to-layer critical path is  wait(epi_done) -> tcgen05.mma ... -> commit(mma_done)
+        {
             int wu_s = 0, wu_par = 0, au_s = 0, au_par = 0;  // consumer-side stage index and round parity
-            uint32_t epi_par = 0;
+            uint32_t epi_par = 0, prof_par = 0;
             bool first = true;
             for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < p.nlayers; ++l) {
                     const int Nl = p.N[l], KBl = p.K[l] >> 6;
                     const int nchunks = (Nl + p.nch - 1) / p.nch;
-                    // operands of the first block first (usually long landed), then the previous epilogue
-                    if (l == 0) mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
-                    mb_wait(w_full + 8 * wu_s, (uint32_t)wu_par);
+                    // every operand wait that can be satisfied from what the rings already hold is done BEFORE the
+                    // epilogue hand-off, so that after it the loop is  tcgen05.mma x4 + commit  per block
+                    const int nblk = KBl * nchunks;
+                    const int pre_w = nblk < p.w_stages ? nblk : p.w_stages;
+                    const int pre_a = (l == 0) ? (KBl < p.a_stages ? KBl : p.a_stages) : 0;
+                    for (int i = 0, st = au_s, pr = au_par; i < pre_a; ++i) {
+                        mb_wait(a_full + 8 * st, (uint32_t)pr);
+                        if (++st == p.a_stages) { st = 0; pr ^= 1; }
+                    }
+                    for (int i = 0, st = wu_s, pr = wu_par; i < pre_w; ++i) {
+                        mb_wait(w_full + 8 * st, (uint32_t)pr);
+                        if (++st == p.w_stages) { st = 0; pr ^= 1; }
+                    }
+                    const int last_rows = Nl - (nchunks - 1) * p.nch;
+                    const uint32_t idesc_full = instr_desc(128, p.nch), idesc_last = instr_desc(128, last_rows);
+                    const uint32_t a_base = (l == 0) ? 0u : R[(l - 1) & 1];
                     if (!first) { mb_wait(epi_done, epi_par); epi_par ^= 1; }  // TMEM drained, next A operand written
                     first = false;
+                    long long mt0 = 0;
+                    if (p.prof) mt0 = clock64();
                     tc_fence_after();
+                    int blk = 0;
                     for (int kb = 0; kb < KBl; ++kb) {
                         uint32_t a_addr;
                         if (l == 0) {
-                            if (kb) mb_wait(a_full + 8 * au_s, (uint32_t)au_par);
+                            if (kb >= pre_a) { mb_wait(a_full + 8 * au_s, (uint32_t)au_par); tc_fence_after(); }
                             a_addr = aring + au_s * kTileBytes;
                         } else {
-                            a_addr = R[(l - 1) & 1] + kb * kTileBytes;
+                            a_addr = a_base + kb * kTileBytes;
                         }
                         const uint64_t ad = smem_desc(a_addr);
-                        for (int nc = 0; nc < nchunks; ++nc) {
+                        for (int nc = 0; nc < nchunks; ++nc, ++blk) {
                             const int s = wu_s;
-                            if (kb | nc) mb_wait(w_full + 8 * s, (uint32_t)wu_par);
-                            tc_fence_after();
-                            const int nrows = min(p.nch, Nl - nc * p.nch);
-                            const uint32_t idesc = instr_desc(128, nrows);
+                            if (blk >= pre_w) { mb_wait(w_full + 8 * s, (uint32_t)wu_par); tc_fence_after(); }
+                            const uint32_t idesc = (nc == nchunks - 1) ? idesc_last : idesc_full;
                             const uint64_t bd = smem_desc(wring + s * p.stage_bytes);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
-                                tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-                            tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
+                                if (elect_one()) tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                            if (elect_one()) tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
                             if (++wu_s == p.w_stages) { wu_s = 0; wu_par ^= 1; }
                         }
                         if (l == 0) {
-                            tc_commit(a_empty + 8 * au_s);
+                            if (elect_one()) tc_commit(a_empty + 8 * au_s);
                             if (++au_s == p.a_stages) { au_s = 0; au_par ^= 1; }
                         }
                     }
-                    tc_commit(mma_done);
+                    if (elect_one()) tc_commit(mma_done);
+                    if (p.prof && blockIdx.x == 0 && lane == 0) {  // profiling only: how long issuing takes, and how long the MMAs take to drain
+                        long long mt1 = clock64();
+                        mb_wait(mma_done, prof_par);
+                        prof_par ^= 1;
+                        long long mt2 = clock64();
+                        atomicAdd((unsigned long long *)p.prof + 5, (unsigned long long)(mt1 - mt0));
+                        atomicAdd((unsigned long long *)p.prof + 6, (unsigned long long)(mt2 - mt1));
+                    }
                 }
             }
         }
@@ -370,7 +401,8 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             if (p.prof) pt3 = clock64();
             tc_fence_before();
             fence_proxy_async();  // epilogue st.shared -> visible to the tensor core's async-proxy reads
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done) : "memory");  // hand the tile back to the MMA issuer
+            __syncwarp();  // orders every lane's stores + proxy fence before the elected lane's arrive
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done) : "memory");  // tile back to the MMA issuer
             if (p.prof && blockIdx.x == 0 && tid == 0) {
                 long long pt4 = clock64();
                 atomicAdd((unsigned long long *)p.prof + 0, (unsigned long long)(pt1 - pt0));  // issue (loads + MMAs)

@@ -25,6 +25,7 @@ class _Lane:
         self.xyz = torch.zeros((batch, npoints, 3), dtype=torch.float32, device=dev)
         self.col = torch.zeros((batch, npoints, cin), dtype=torch.float32, device=dev)
         self.out = None
+        self.out_h = None  # bf16 copy of the feature map (bf16 path)
         self.graph = None
         self.done = torch.cuda.Event()
 
@@ -43,17 +44,18 @@ class BackboneEngine:
                 lane.xyz.copy_(warm_inputs[0]); lane.col.copy_(warm_inputs[1])
             torch.cuda.synchronize(self.dev)
             with torch.cuda.stream(lane.stream):
-                lane.out = self._forward(lane)  # eager warm-up: packs weights, folds BN, sets kernel attributes
+                lane.out, lane.out_h = self._forward(lane)  # eager warm-up: packs weights, folds BN, sets kernel attributes
             lane.stream.synchronize()
             if use_graphs:
                 lane.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(lane.graph, stream=lane.stream, capture_error_mode="relaxed"):
-                    lane.out = self._forward(lane)
+                    lane.out, lane.out_h = self._forward(lane)
         torch.cuda.synchronize(self.dev)
 
     def _forward(self, lane):
-        return backbone.forward(lane.xyz, lane.col, self.store, sa_specs=self.sa_specs, fp_specs=self.fp_specs,
-                                precision=self.precision)["l0_points"]
+        r = backbone.forward(lane.xyz, lane.col, self.store, sa_specs=self.sa_specs, fp_specs=self.fp_specs,
+                             precision=self.precision, l0_bf16=True)
+        return r["l0_points"], r.get("l0_points_bf16")
 
     def submit(self, xyz, colour, after=None):
         """Enqueue one batch on the next lane. xyz/colour: device tensors or pinned host tensors."""
@@ -68,7 +70,7 @@ class BackboneEngine:
             if lane.graph is not None:
                 lane.graph.replay()
             else:
-                lane.out = self._forward(lane)
+                lane.out, lane.out_h = self._forward(lane)
             lane.done.record(lane.stream)
         return i
 
@@ -76,9 +78,11 @@ class BackboneEngine:
         return self.lanes[ticket].out
 
     def result_to_host(self, ticket, pinned_out):
+        """Async D2H of the lane's feature map on the lane's stream; a bfloat16 `pinned_out` takes the bf16 map."""
         lane = self.lanes[ticket]
+        src = lane.out_h if (pinned_out.dtype == torch.bfloat16 and lane.out_h is not None) else lane.out
         with torch.cuda.stream(lane.stream):
-            pinned_out.copy_(lane.out, non_blocking=True)
+            pinned_out.copy_(src, non_blocking=True)
             lane.done.record(lane.stream)
 
     def join(self, onto=None):

@@ -111,8 +111,8 @@ def sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz, sto
     return idx, out
 
 
-def fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers):
-    """-> (b,n,cout) f32."""
+def fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers, want_bf16=False):
+    """-> (b,n,cout) f32  (and the same map in bf16 when want_bf16)."""
     from .pointnet_util import _stage, _run_mlp_f32
     b, n, _ = idx.shape
     m, c2 = points2.shape[1], points2.shape[2]
@@ -136,5 +136,7 @@ def fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers):
         check(L.gspn_fp_assemble(b, n, m, c1, c2, None if p1 is None else p1.data_ptr(), points2.contiguous().data_ptr(), idx.data_ptr(),
                                  weight.data_ptr(), img.data_ptr(), ld, _stream()), "fp_assemble")
     with _stage(timers, scope + ":mlp"):
-        out, _ = mlp_chain(img, rows, ld, layers, None, 1)
+        out, out_h = mlp_chain(img, rows, ld, layers, None, 1, want_bf16=want_bf16)
+    if want_bf16:
+        return out.reshape(b, n, out.shape[-1]), out_h.reshape(b, n, out_h.shape[-1])
     return out.reshape(b, n, out.shape[-1])

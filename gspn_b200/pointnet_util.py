@@ -207,8 +207,9 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
 
 
 def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, reuse=False, variables=None,
-                       precision=None, timers=None):
-    """-> new_points1 (b,n,mlp[-1])  (or the concatenated (b,n,c2+c1) map when mlp == [])."""
+                       precision=None, timers=None, also_bf16=False):
+    """-> new_points1 (b,n,mlp[-1])  (or the concatenated (b,n,c2+c1) map when mlp == []).
+    also_bf16 (extension, bf16 path only): return (f32 map, bf16 map) -- the tensor-core chain emits both."""
     _check_unbuilt(is_training)
     store = VARIABLES if variables is None else variables
     precision = precision or DEFAULT_PRECISION
@@ -220,7 +221,7 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
         _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
     if precision == "bf16" and layers:
         from . import mlp_tc
-        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers)
+        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers, want_bf16=also_bf16)
     with _stage(timers, scope + ":interpolate"):
         interpolated = ops.three_interpolate(points2, idx, weight)
         new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated

@@ -177,9 +177,9 @@ int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a,
                    const void *const *wimg, const float *const *scale, const float *const *shift,
                    const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream);
 
-/* Tuning door: when prof5 (device, 5 x int64, zeroed by the caller) is non-NULL, later gspn_mlp_chain launches add
- * CTA 0 / thread 0's cycle counts: [0] load+MMA issue, [1] MMA completion wait, [2] epilogue, [3] fences+barrier,
- * [4] number of layer-steps.  NULL switches it off. */
+/* Tuning door: when prof (device, 8 x int64, zeroed by the caller) is non-NULL, later gspn_mlp_chain launches add CTA 0's
+ * cycle counts: epilogue thread 0: [1] wait for the MMAs, [2] epilogue, [3] fences+hand-off, [4] number of layer-steps;
+ * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands.  NULL switches it off. */
 void gspn_mlp_chain_set_profile(long long *prof5);
 
 /* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of
