@@ -640,3 +640,24 @@ def test_grid_nn_distance_equals_ordered_scan(cuda, oracle, kind):
         for g, s_, e in zip(got, scan, exp):
             assert np.array_equal(bits(g), bits(s_)), rounding
             assert np.array_equal(bits(g[:1]), bits(e)), rounding
+
+
+# ------------------------------------------------------------------------------------ executor
+def test_graph_engine_matches_eager_forward(cuda):
+    """CUDA-graph lanes on separate streams give exactly what the eager in-order forward gives."""
+    from gspn_b200 import backbone
+    from gspn_b200.engine import BackboneEngine
+    specs = backbone.scaled_sa_specs(8192)
+    store, _ = backbone.random_variables(cuda, sa_specs=specs)
+    batches = [scenes.scannet_like_batch(90 + 2 * i, 2, 8192) for i in range(3)]
+    eng = BackboneEngine(store, 2, 8192, precision="bf16", depth=2, device=cuda, sa_specs=specs)
+    for xyz, col in batches:
+        want = backbone.forward(T(xyz, cuda), T(col, cuda), store, sa_specs=specs, precision="bf16", l0_bf16=True)
+        tk = eng.submit(T(xyz, cuda), T(col, cuda))
+        eng.synchronize()
+        assert torch.equal(eng.result(tk), want["l0_points"])
+        assert torch.equal(eng.lanes[tk].out_h, want["l0_points_bf16"])
+        host = torch.empty(eng.lanes[tk].out_h.shape, dtype=torch.bfloat16).pin_memory()
+        eng.result_to_host(tk, host)
+        eng.synchronize()
+        assert torch.equal(host, want["l0_points_bf16"].cpu())

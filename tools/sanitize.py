@@ -1,0 +1,33 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck / synccheck).
+   compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gspn_b200
+from gspn_b200 import backbone, context_encoder, scenes
+dev = torch.device("cuda:0")
+xyz, col = scenes.scannet_like_batch(0, 2, 4608)
+x, c = torch.from_numpy(xyz).to(dev), torch.from_numpy(col).to(dev)
+specs = backbone.scaled_sa_specs(4608)
+store, _ = backbone.random_variables(dev, sa_specs=specs)
+for prec in ("bf16", "fp32"):
+    out = backbone.forward(x, c, store, sa_specs=specs, precision=prec, l0_bf16=True)
+torch.cuda.synchronize()
+fps = gspn_b200.farthest_point_sample(16, x)
+context_encoder.multi_encoding_net(x, c, 16, [0.5, 1.0], [64, 128], [[64, 128, 256]] * 2, [], False, None, "ctx", use_xyz=True, fps_idx=fps,
+                                   variables=store)
+a = torch.randn(2, 3000, 3, device=dev, requires_grad=True)
+b = torch.randn(2, 2500, 3, device=dev, requires_grad=True)
+d1, i1, d2, i2 = gspn_b200.nn_distance(a, b)
+(d1.sum() + d2.sum()).backward()
+p = torch.randn(2, 300, 16, device=dev, requires_grad=True)
+idx, _ = gspn_b200.query_ball_point(0.5, 8, x[:, :300].contiguous(), x[:, :40].contiguous())
+gspn_b200.group_point(p, idx).sum().backward()
+dist, i3 = gspn_b200.three_nn(x[:, :500].contiguous(), x[:, :300].contiguous())
+w = torch.full((2, 500, 3), 1 / 3, device=dev)
+gspn_b200.three_interpolate(p, i3, w).sum().backward()
+gspn_b200.gather_point(p, fps % 300).sum().backward()
+big = torch.rand(1, 140000, 3, device=dev)
+gspn_b200.farthest_point_sample(8, big)
+torch.cuda.synchronize()
+print("sanitize workload done")
