@@ -48,6 +48,12 @@ SIGNATURES = {
     "gspn_mlp_pack_weights": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "gspn_mlp_chain": (c_int, [c_long, c_int, P, P, P, P, P, P, c_int, P, P, P]),
     "gspn_mlp_chain_set_profile": (None, [P]),
+    "gspn_col_moments_f32": (c_int, [c_long, c_int, P, P, P, P]),
+    "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),
+    "gspn_maxpool_argmax_f32": (c_int, [c_long, c_int, c_int, P, P, P, P]),
+    "gspn_bn_act_pool_bwd_f32": (c_int, [c_long, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "gspn_mlp_wgrad_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, P]),
+    "gspn_group_rows_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
 }
 

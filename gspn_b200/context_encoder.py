@@ -18,6 +18,8 @@ def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list,
                        use_xyz=False, output_shift=False, shift_pred=None, fps_idx=None, variables=None, precision=None):
     """-> (new_xyz (b,npoint,3), new_points (b,npoint,sum mlp[-1]), shift_pred, fps_idx)."""
     pu._check_unbuilt(is_training)
+    if is_training:
+        raise NotImplementedError("multi_encoding_net: the training form is built for pointnet_sa_module / pointnet_fp_module only")
     if mlp_list2 or output_shift:
         raise NotImplementedError("mlp_list2 / output_shift are conv1d head code outside the SA/FP path (reference call site uses neither)")
     store = pu.VARIABLES if variables is None else variables

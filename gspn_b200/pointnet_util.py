@@ -17,8 +17,9 @@ tf.get_variable would, later calls reuse them.  Two execution precisions share e
   precision='fp32' : reference-precision MLP on CUDA cores (parity tolerance 1e-5),
   precision='bf16' : tcgen05 tensor-core MLP chain fed by the fused ball-query+group tile image.
 
-Not built: is_training=True (batch-statistics BN + backward), knn=True,
-tnet_spec (undefined `tnet` in the reference itself, pointnet_util.py:44), pooling other than
+is_training=True runs the fp32 training form (gspn_b200/train.py): batch-statistics batch norm with in-place moving
+average updates, autograd through MLP, max-pool, grouping and interpolation.
+Not built: knn=True, tnet_spec (undefined `tnet` in the reference itself, pointnet_util.py:44), pooling other than
 'max' (no call site in the model).  Those raise NotImplementedError instead of approximating.
 """
 import math
@@ -102,8 +103,6 @@ def _stage(timers, name):
 
 
 def _check_unbuilt(is_training, knn=False, tnet_spec=None, pooling="max"):
-    if is_training:
-        raise NotImplementedError("is_training=True (batch-statistics BN + backward) is not built yet (SURVEY.md 8f rank 1)")
     if knn:
         raise NotImplementedError("knn=True has no call site in the reference model (SURVEY.md 2.1 row 2)")
     if tnet_spec is not None:
@@ -179,6 +178,11 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     layers = store.layers(scope, "conv", cin, list(mlp), bn)
     layers2 = store.layers(scope, "conv_post_", mlp[-1] if mlp else cin, list(mlp2 or []), bn)
 
+    if is_training:
+        if group_all or mlp2 or not layers:
+            raise NotImplementedError("is_training=True is built for the model's call shape (group_all=False, mlp2=None)")
+        from . import train
+        return train.sa_module_train(xyz, points, npoint, radius, nsample, layers, bn_decay, use_xyz)
     if group_all:
         new_xyz, new_points, idx, _ = sample_and_group_all(xyz, points, use_xyz)
         x = _run_mlp_f32(new_points.reshape(b * n, cin).contiguous(), layers)
@@ -217,6 +221,9 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
     c2 = points2.shape[2]
     c1 = 0 if points1 is None else points1.shape[2]
     layers = store.layers(scope, "conv_", c1 + c2, list(mlp), bn)
+    if is_training:
+        from . import train
+        return train.fp_module_train(xyz1, xyz2, points1, points2, layers, bn_decay)
     with _stage(timers, scope + ":three_nn"):
         _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
     if precision == "bf16" and layers:

@@ -1,0 +1,188 @@
+"""Training form of the SA / FP modules (is_training=True): batch-statistics batch norm, autograd through the shared
+MLP, max-pool, grouping and interpolation.  fp32 on CUDA cores (csrc/train_ops.cu + the fp32 GEMM of mlp_f32.cu);
+torch supplies the autograd tape and a few c-length vector ops, the per-row work is all in this library's kernels.
+
+Reference semantics: tf_util.conv2d -> tf.nn.bias_add -> tf.contrib.layers.batch_norm(center, scale, is_training,
+decay=bn_decay or 0.9, updates_collections=None, epsilon default 1e-3) -> relu (utils/tf_util.py:170-184,515-534);
+moments over every axis but channels; moving averages updated in place every step.
+Gradients flow to the layer variables and to `points` (features), as in the reference's registered gradients
+(GroupPointGrad, ThreeInterpolateGrad, GatherPointGrad); xyz, FPS, ball-query and three_nn indices carry none.
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import check
+
+BN_EPS = 1e-3
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _linear(x, w, shift, y=None):
+    """y = x @ w + shift  (rows,cin)x(cin,cout); fp32 CUDA-core GEMM (gspn_mlp_layer_f32 with scale=1, no activation)."""
+    rows, cin = x.shape
+    cout = w.shape[1]
+    if y is None:
+        y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+    ones = torch.ones(cout, dtype=torch.float32, device=x.device)
+    check(_lib.lib().gspn_mlp_layer_f32(rows, cin, cout, x.data_ptr(), x.stride(0), w.data_ptr(), ones.data_ptr(), shift.data_ptr(), 0, 1,
+                                        y.data_ptr(), _s()), "mlp_layer_f32")
+    return y
+
+
+class MlpLayerTrain(torch.autograd.Function):
+    """act(bn_batch(x@W+b)) [+ max over groups of `pool` rows]; updates moving_mean / moving_variance in place."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, gamma, beta, moving_mean, moving_var, decay, pool, relu):
+        L = _lib.lib()
+        x = x.contiguous() if x.stride(1) != 1 else x
+        w = w.contiguous()
+        rows, cin = x.shape
+        cout = w.shape[1]
+        dev = x.device
+        bn = gamma is not None
+        z = _linear(x, w, bias.contiguous())
+        if bn:
+            s1 = torch.empty(cout, dtype=torch.float64, device=dev)
+            s2 = torch.empty(cout, dtype=torch.float64, device=dev)
+            check(L.gspn_col_moments_f32(rows, cout, z.data_ptr(), s1.data_ptr(), s2.data_ptr(), _s()), "col_moments")
+            mean64 = s1 / rows
+            var64 = (s2 / rows - mean64 * mean64).clamp_(min=0.0)  # biased variance normalises (tf.nn.moments)
+            mean, invstd = mean64.float(), torch.rsqrt(var64.float() + BN_EPS)
+            with torch.no_grad():  # moving averages, updates_collections=None: updated as part of the forward
+                moving_mean.mul_(decay).add_(mean * (1.0 - decay))
+                moving_var.mul_(decay).add_(var64.float() * (1.0 - decay))
+            g, be = gamma.contiguous(), beta.contiguous()
+        else:
+            mean = torch.zeros(cout, device=dev)
+            invstd = torch.ones(cout, device=dev)
+            g, be = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+        y = torch.empty_like(z)
+        check(L.gspn_bn_act_f32(rows, cout, z.data_ptr(), mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), be.data_ptr(), int(relu), y.data_ptr(),
+                                _s()), "bn_act")
+        argmax = None
+        out = y
+        if pool > 1:
+            groups = rows // pool
+            out = torch.empty((groups, cout), dtype=torch.float32, device=dev)
+            argmax = torch.empty((groups, cout), dtype=torch.int32, device=dev)
+            check(L.gspn_maxpool_argmax_f32(groups, pool, cout, y.data_ptr(), out.data_ptr(), argmax.data_ptr(), _s()), "maxpool_argmax")
+        ctx.save_for_backward(x, w, z, mean, invstd, g, be, argmax)
+        ctx.meta = (pool, int(relu), bn)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        x, w, z, mean, invstd, g, be, argmax = ctx.saved_tensors
+        pool, relu, bn = ctx.meta
+        rows, cin = x.shape
+        cout = w.shape[1]
+        dev = x.device
+        dout = dout.contiguous()
+        s1 = torch.empty(cout, dtype=torch.float64, device=dev)
+        s2 = torch.empty(cout, dtype=torch.float64, device=dev)
+        dz = torch.empty((rows, cout), dtype=torch.float32, device=dev)
+        check(L.gspn_bn_act_pool_bwd_f32(rows, cout, pool, relu, int(bn), z.data_ptr(), dout.data_ptr(), None if argmax is None else argmax.data_ptr(),
+                                         mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), be.data_ptr(), s1.data_ptr(), s2.data_ptr(),
+                                         dz.data_ptr(), None, None, _s()), "bn_act_pool_bwd")
+        dW = torch.empty((cin, cout), dtype=torch.float32, device=dev)
+        db = torch.empty(cout, dtype=torch.float32, device=dev)
+        check(L.gspn_mlp_wgrad_f32(rows, cin, cout, x.data_ptr(), x.stride(0), dz.data_ptr(), dW.data_ptr(), db.data_ptr(), _s()), "mlp_wgrad")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _linear(dz, w.t().contiguous(), torch.zeros(cin, device=dev))
+        dgamma = s2.float() if bn else None
+        dbeta = s1.float() if bn else None
+        return dx, dW, db, dgamma, dbeta, None, None, None, None, None
+
+
+class GroupRowsTrain(torch.autograd.Function):
+    """Fused ball query + group -> fp32 rows [features | xyz - centre]; gradient to the features only."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, points, radius, nsample):
+        idx, _, grouped, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
+        ctx.save_for_backward(idx)
+        ctx.shape = None if points is None else tuple(points.shape)
+        ctx.ld = ld
+        ctx.mark_non_differentiable(idx)
+        return grouped, idx
+
+    @staticmethod
+    def backward(ctx, dgrouped, _didx):
+        (idx,) = ctx.saved_tensors
+        if ctx.shape is None:
+            return None, None, None, None, None
+        b, n, c = ctx.shape
+        _, m, k = idx.shape
+        dgrouped = dgrouped.contiguous()
+        dp = torch.empty((b, n, c), dtype=torch.float32, device=dgrouped.device)
+        check(_lib.lib().gspn_group_rows_grad(b, n, c, m, k, ctx.ld, dgrouped.data_ptr(), idx.data_ptr(), dp.data_ptr(), _s()), "group_rows_grad")
+        return None, None, dp, None, None
+
+
+def run_mlp_train(x2d, layers, bn_decay, pool_last=1, first_weight=None):
+    decay = 0.9 if bn_decay is None else float(bn_decay)  # utils/tf_util.py:528
+    for i, layer in enumerate(layers):
+        w = first_weight if (i == 0 and first_weight is not None) else layer["weights"]
+        pool = pool_last if i == len(layers) - 1 else 1
+        x2d = MlpLayerTrain.apply(x2d, w, layer["biases"], layer.get("gamma"), layer.get("beta"), layer.get("moving_mean"),
+                                  layer.get("moving_variance"), decay, pool, True)
+    return x2d
+
+
+def sa_module_train(xyz, points, npoint, radius, nsample, layers, bn_decay, use_xyz=True):
+    """pointnet_sa_module(is_training=True), pooling='max', mlp2=None, group_all=False."""
+    b, n, _ = xyz.shape
+    fps_idx = ops.farthest_point_sample(npoint, xyz)
+    new_xyz = ops.gather_point(xyz, fps_idx)
+    grouped, idx = GroupRowsTrain.apply(xyz, new_xyz.detach(), points, radius, nsample)
+    w = layers[0]["weights"]
+    if points is not None:  # grouped columns are [features | xyz]; the reference kernel rows are [xyz | features]
+        w = torch.cat([w[3:], w[:3]], dim=0) if use_xyz else torch.cat([w, torch.zeros((3, w.shape[1]), device=w.device)], dim=0)
+    x = run_mlp_train(grouped, layers, bn_decay, pool_last=nsample, first_weight=w)
+    return new_xyz, x.reshape(b, npoint, x.shape[-1]), idx
+
+
+def fp_module_train(xyz1, xyz2, points1, points2, layers, bn_decay):
+    """pointnet_fp_module(is_training=True)."""
+    b, n, _ = xyz1.shape
+    _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
+    interpolated = ops.three_interpolate(points2, idx, weight)
+    x = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
+    if not layers:
+        return x
+    y = run_mlp_train(x.reshape(b * n, x.shape[2]), layers, bn_decay)
+    return y.reshape(b, n, y.shape[-1])
+
+
+def trainable(store):
+    """Mark every weight / bias / gamma / beta of a VariableStore as requiring grad; returns the list of leaves."""
+    leaves = []
+    for layers in store.values():
+        for layer in layers:
+            for k in ("weights", "biases", "gamma", "beta"):
+                if layer.get(k) is not None:
+                    layer[k].requires_grad_(True)
+                    leaves.append(layer[k])
+    return leaves
+
+
+def allreduce_gradients(params, group=None):
+    """Data-parallel step: ONE bucketed all-reduce (mean) of every parameter gradient per step.
+    Works with any initialised torch.distributed backend (NCCL on the GPUs, gloo in the CPU test)."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].reshape(g.shape))
+        o += g.numel()

@@ -177,6 +177,30 @@ int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a,
                    const void *const *wimg, const float *const *scale, const float *const *shift,
                    const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream);
 
+/* ---- training form of the shared MLP (fp32): conv 1x1 + bias -> batch norm over the BATCH moments
+ * (tf.contrib.layers.batch_norm, is_training=True, utils/tf_util.py:515-534) -> ReLU -> reduce_max, and its backward.
+ * The GEMMs are gspn_mlp_layer_f32 (forward: scale=1, shift=bias, relu=0; dX: the same with W^T). */
+/* sum[c] = sum_r z[r,c], sumsq[c] = sum_r z[r,c]^2 in double (zeroed here). */
+int gspn_col_moments_f32(long rows, int c, const float *z, double *sum, double *sumsq, gspn_stream_t stream);
+/* y = act((z-mean)*invstd*gamma+beta) */
+int gspn_bn_act_f32(long rows, int c, const float *z, const float *mean, const float *invstd, const float *gamma, const float *beta,
+                    int relu, float *y, gspn_stream_t stream);
+/* out[g,c] = max_s y[g*k+s,c], argmax[g,c] = the winning s (first maximum). */
+int gspn_maxpool_argmax_f32(long groups, int k, int c, const float *y, float *out, int *argmax, gspn_stream_t stream);
+/* backward of pool(act(bn(z))): dy is (rows/pool, c) when pool>1 (argmax from the forward) else (rows, c).
+ * Writes s1[c] = sum dy' (= dbeta), s2[c] = sum dy'*xhat (= dgamma) in double and dz (rows,c). dgamma/dbeta unused (NULL).
+ * bn=0: layer without batch norm (pass mean=0, invstd=gamma=1, beta=0): dz = dy'. */
+int gspn_bn_act_pool_bwd_f32(long rows, int c, int pool, int relu, int bn, const float *z, const float *dy, const int *argmax,
+                             const float *mean, const float *invstd, const float *gamma, const float *beta,
+                             double *s1, double *s2, float *dz, float *dgamma, float *dbeta, gspn_stream_t stream);
+/* dW (cin,cout) = x^T dz, dbias (cout, may be NULL) = colsum(dz); both zeroed here; x has row stride ldx. */
+int gspn_mlp_wgrad_f32(long rows, int cin, int cout, const float *x, int ldx, const float *dz, float *dW, float *dbias,
+                       gspn_stream_t stream);
+/* backward of the fused grouping w.r.t. the features: grad_points (b,n,c) (zeroed here) += grad_rows[(b,j,s), :c]
+ * (rows of stride ld, features first) scattered through idx (b,m,nsample); GroupPointGrad tf_grouping_g.cu:66-83. */
+int gspn_group_rows_grad(int b, int n, int c, int m, int nsample, int ld, const float *grad_rows, const int *idx,
+                         float *grad_points, gspn_stream_t stream);
+
 /* Tuning door: when prof (device, 8 x int64, zeroed by the caller) is non-NULL, later gspn_mlp_chain launches add CTA 0's
  * cycle counts: epilogue thread 0: [1] wait for the MMAs, [2] epilogue, [3] fences+hand-off, [4] number of layer-steps;
  * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands.  NULL switches it off. */

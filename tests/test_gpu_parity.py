@@ -414,7 +414,7 @@ def test_pointnet_fp_module_fp32_matches_oracle(cuda, oracle, mlp, with_p1):
 def test_unbuilt_variants_raise(cuda):
     x = torch.zeros(1, 64, 3, device=cuda)
     with pytest.raises(NotImplementedError):
-        gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], None, False, True, None, "t1")
+        gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], [8], False, True, None, "t1")  # training form with mlp2
     with pytest.raises(NotImplementedError):
         gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], None, False, False, None, "t2", pooling="avg")
 
@@ -661,3 +661,98 @@ def test_graph_engine_matches_eager_forward(cuda):
         eng.result_to_host(tk, host)
         eng.synchronize()
         assert torch.equal(host, want["l0_points_bf16"].cpu())
+
+
+# ------------------------------------------------------------------------------------ training form (config 4 building blocks)
+def torch_mlp_train(x, layers, decay, pool):
+    """Plain PyTorch fp32 reference of conv1x1+bias -> BN(batch moments, eps 1e-3) -> ReLU [-> max over pool rows]."""
+    import torch.nn.functional as F
+    for i, l in enumerate(layers):
+        z = x @ l["weights"] + l["biases"]
+        z = F.batch_norm(z, l["moving_mean"], l["moving_variance"], l["gamma"], l["beta"], training=True, momentum=1.0 - decay, eps=1e-3)
+        x = torch.relu(z)
+    if pool > 1:
+        x = x.reshape(-1, pool, x.shape[-1]).max(dim=1).values
+    return x
+
+
+def clone_layers(layers_np, dev, grad=True):
+    out = []
+    for l in layers_np:
+        d = {k: T(v, dev) for k, v in l.items()}
+        if grad:
+            for k in ("weights", "biases", "gamma", "beta"):
+                d[k].requires_grad_(True)
+        out.append(d)
+    return out
+
+
+TRAIN_TOL = dict(rtol=2e-3, atol=2e-4)  # fp32 both sides; atomics + different reduction orders (reference's own grad tests: 1e-4 abs)
+
+
+def test_sa_module_training_forward_backward(cuda, oracle):
+    rng = np.random.RandomState(0)
+    xyz, _ = scenes.scannet_like_batch(100, 2, 2048)
+    feats = rng.randn(2, 2048, 16).astype(np.float32)
+    layers_np = rand_layers(rng, 19, [32, 32, 64])
+    m, r, k = 128, 0.3, 32
+    # ours
+    mine = clone_layers(layers_np, cuda)
+    st = pu.VariableStore(device=cuda)
+    st["sa/conv"] = mine
+    st["sa/conv_post_"] = []
+    f = T(feats, cuda).requires_grad_(True)
+    nx, out, idx = gspn_b200.pointnet_sa_module(T(xyz, cuda), f, m, r, k, [32, 32, 64], None, False, True, 0.9, "sa", variables=st)
+    gout = T(rng.randn(*out.shape).astype(np.float32), cuda)
+    out.backward(gout)
+    # torch reference on the oracle's indices
+    enx, new_points, eidx, _ = oracle.sample_and_group(m, r, k, xyz, feats)
+    assert np.array_equal(N(idx), eidx)
+    ref = clone_layers(layers_np, cuda)
+    fr = T(feats, cuda).requires_grad_(True)
+    ii = T(eidx.astype(np.int64), cuda)
+    gx = torch.stack([T(xyz, cuda)[b][ii[b]] for b in range(2)]) - T(enx, cuda).unsqueeze(2)
+    gp = torch.stack([fr[b][ii[b]] for b in range(2)])
+    x = torch.cat([gx, gp], dim=-1).reshape(-1, 19)
+    want = torch_mlp_train(x, ref, 0.9, k).reshape(2, m, 64)
+    want.backward(gout)
+    np.testing.assert_allclose(N(out), N(want), **TRAIN_TOL)
+    np.testing.assert_allclose(N(f.grad), N(fr.grad), **TRAIN_TOL)
+    for a, b_ in zip(mine, ref):
+        for key in ("weights", "biases", "gamma", "beta"):
+            np.testing.assert_allclose(N(a[key].grad), N(b_[key].grad), rtol=2e-3, atol=5e-4, err_msg=key)
+        np.testing.assert_allclose(N(a["moving_mean"]), N(b_["moving_mean"]), rtol=1e-4, atol=1e-5)
+    # the inference form afterwards uses the updated moving averages
+    _, out_inf, _ = gspn_b200.pointnet_sa_module(T(xyz, cuda), T(feats, cuda), m, r, k, [32, 32, 64], None, False, False, None, "sa", variables=st,
+                                                 precision="fp32")
+    assert out_inf.shape == out.shape
+
+
+def test_fp_module_training_forward_backward(cuda, oracle):
+    rng = np.random.RandomState(1)
+    xyz1 = scenes.scannet_like_batch(101, 2, 1024)[0]
+    xyz2 = oracle.gather_point(xyz1, oracle.farthest_point_sample(256, xyz1))
+    p1 = rng.randn(2, 1024, 8).astype(np.float32)
+    p2 = rng.randn(2, 256, 32).astype(np.float32)
+    layers_np = rand_layers(rng, 40, [64, 32])
+    mine = clone_layers(layers_np, cuda)
+    st = pu.VariableStore(device=cuda)
+    st["fp/conv_"] = mine
+    a1, a2 = T(p1, cuda).requires_grad_(True), T(p2, cuda).requires_grad_(True)
+    out = gspn_b200.pointnet_fp_module(T(xyz1, cuda), T(xyz2, cuda), a1, a2, [64, 32], True, None, "fp", variables=st)
+    gout = T(rng.randn(*out.shape).astype(np.float32), cuda)
+    out.backward(gout)
+    ed, ei = oracle.three_nn(xyz1, xyz2)
+    w = T(oracle.fp_weights(ed), cuda)
+    ref = clone_layers(layers_np, cuda)
+    b1, b2 = T(p1, cuda).requires_grad_(True), T(p2, cuda).requires_grad_(True)
+    ii = T(ei.astype(np.int64), cuda)
+    interp = torch.stack([(b2[b][ii[b]] * w[b].unsqueeze(-1)).sum(1) for b in range(2)])
+    want = torch_mlp_train(torch.cat([interp, b1], dim=2).reshape(-1, 40), ref, 0.9, 1).reshape(2, 1024, 32)
+    want.backward(gout)
+    np.testing.assert_allclose(N(out), N(want), **TRAIN_TOL)
+    np.testing.assert_allclose(N(a1.grad), N(b1.grad), **TRAIN_TOL)
+    np.testing.assert_allclose(N(a2.grad), N(b2.grad), **TRAIN_TOL)
+    for a, b_ in zip(mine, ref):
+        for key in ("weights", "biases", "gamma", "beta"):
+            np.testing.assert_allclose(N(a[key].grad), N(b_[key].grad), rtol=2e-3, atol=5e-4, err_msg=key)

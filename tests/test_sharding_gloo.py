@@ -63,3 +63,32 @@ def test_two_rank_gloo_sharding():
         expect.append(int(abs(float(xyz.sum())) * 1000) + 1)
     assert owned == expect  # each scene built by exactly one rank
     assert tmax == 2.0
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gspn_b200.train import allreduce_gradients
+    params = [torch.zeros(3, 4), torch.zeros(5), torch.zeros(2, 2)]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    params[2].grad = None  # parameters without a gradient are skipped consistently on every rank
+    allreduce_gradients(params)
+    if rank == 0:
+        q.put([None if p.grad is None else p.grad.flatten()[0].item() for p in params])
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    """Config 4's only collective: one bucketed mean all-reduce of the MLP/BN gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [1.5, 3.0, None]  # mean over ranks of (rank+1)*(i+1)
