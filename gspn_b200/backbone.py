@@ -54,7 +54,8 @@ def random_variables(device, colour_channels=3, seed=7, bn_seed=8, sa_specs=SA_S
     return store, as_numpy
 
 
-def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=None, timers=None, l0_bf16=False):
+def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=None, timers=None, l0_bf16=False, is_training=False,
+            bn_decay=None):
     """xyz (b,n,3), colour (b,n,c) CUDA f32 -> dict(l0_points (b,n,128), l1..l4 xyz/points, indices).
     timers: optional callable(name) -> context manager, used by bench.py to bracket stages with CUDA events."""
     def stage(name):
@@ -62,7 +63,7 @@ def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=
     xs, ps, idxs = [xyz], [colour], []
     for i, (m, r, k, mlp) in enumerate(sa_specs):
         with stage("sa%d" % (i + 1)):
-            nx, npts, idx = pu.pointnet_sa_module(xs[-1], ps[-1], m, r, k, mlp, None, False, False, None, "layer%d" % (i + 1),
+            nx, npts, idx = pu.pointnet_sa_module(xs[-1], ps[-1], m, r, k, mlp, None, False, is_training, bn_decay, "layer%d" % (i + 1),
                                                   variables=store, precision=precision, timers=timers)
         xs.append(nx)
         ps.append(npts)
@@ -72,8 +73,8 @@ def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=
         lvl = 3 - i
         want_h = l0_bf16 and i == len(fp_specs) - 1 and (precision or pu.DEFAULT_PRECISION) == "bf16"
         with stage("fp%d" % (i + 1)):
-            up = pu.pointnet_fp_module(xs[lvl], xs[lvl + 1], ps[lvl], up, mlp, False, None, "fa_layer%d" % (i + 1), variables=store,
-                                       precision=precision, timers=timers, also_bf16=want_h)
+            up = pu.pointnet_fp_module(xs[lvl], xs[lvl + 1], ps[lvl], up, mlp, is_training, bn_decay, "fa_layer%d" % (i + 1), variables=store,
+                                       precision=precision, timers=timers, also_bf16=want_h and not is_training)
     out = {"xyz": xs, "points": ps, "idx": idxs}
     if isinstance(up, tuple):
         out["l0_points"], out["l0_points_bf16"] = up
