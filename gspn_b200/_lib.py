@@ -47,6 +47,7 @@ SIGNATURES = {
     "gspn_mlp_weight_image_bytes": (c_size_t, [c_int, c_int]),
     "gspn_mlp_pack_weights": (c_int, [c_int, c_int, c_int, P, P, P, P]),
     "gspn_mlp_chain": (c_int, [c_long, c_int, P, P, P, P, P, P, c_int, P, P, P]),
+    "gspn_mlp_chain_gather": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, c_int, P, P, P]),
     "gspn_mlp_chain_set_profile": (None, [P]),
     "gspn_col_moments_f32": (c_int, [c_long, c_int, P, P, P, P]),
     "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),

@@ -43,6 +43,14 @@ struct ChainParams {
     int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
     uint32_t r0_bytes, r1_bytes, stage_bytes;
     long long *prof;  // optional: per-phase cycle counters of CTA 0 / thread 0 (tools/tc_profile.py)
+    // gather mode (a == nullptr): layer 0's operand rows [features(c) | xyz - centre - shift | 0] (c+3 <= 8, K0 = 64) are built
+    // in shared memory by the input-producer warp straight from the ball-query indices -- no tile image in HBM at all
+    const int *g_idx;      // (b, m, nsample)
+    const float *g_xyz;    // (b, n, 3)
+    const float *g_ctr;    // (b, m, 3)
+    const float *g_shift;  // (b, m, 3) or null
+    const float *g_pts;    // (b, n, c) f32 or null
+    int g_n, g_m, g_k, g_c;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -175,7 +183,9 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
     {
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *r = reinterpret_cast<uint4 *>(sm);
-        for (uint32_t i = tid; i < (p.r0_bytes + p.r1_bytes) / 16; i += blockDim.x) r[i] = z;
+        // gather mode also zeroes the input ring: each row only ever writes its first 16-byte chunk
+        const uint32_t zbytes = p.r0_bytes + p.r1_bytes + (p.a ? 0u : (uint32_t)p.a_stages * kTileBytes);
+        for (uint32_t i = tid; i < zbytes / 16; i += blockDim.x) r[i] = z;
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_slot)), "r"(p.tmem_cols) : "memory");
@@ -195,7 +205,46 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
 
     // ---- producer warps: one lane each keeps a ring full for the whole kernel, independent of the MMA/epilogue
     // timeline, so the loads of the next layers / tiles are in flight while the epilogue warps are busy
-    if (warp == p.epi_warps) {
+    if (warp == p.epi_warps && p.a == nullptr) {
+        // gather producer: the whole warp; lane L builds rows L, L+32, L+64, L+96 of the tile (one 16-byte chunk each)
+        int s = 0, par = 0;
+        const int c = p.g_c;
+        long t = blockIdx.x;
+        for (int i = 0; i < total_a; ++i, t += gridDim.x) {
+            if (i >= p.a_stages) mb_wait(a_empty + 8 * s, (uint32_t)(par ^ 1));
+            unsigned char *stage = sm + p.r0_bytes + p.r1_bytes + (size_t)s * kTileBytes;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = lane + 32 * rr;
+                const long row = t * kTileRows + r;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (row < p.rows) {
+                    const long q = row / p.g_k;  // global query index cloud*m + j
+                    const long cloud = q / p.g_m;
+                    const int ii = __ldg(p.g_idx + row);
+                    const float *px = p.g_xyz + (cloud * p.g_n + ii) * 3, *cx = p.g_ctr + q * 3;
+                    float d[3], f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        d[a] = __fsub_rn(__ldg(px + a), __ldg(cx + a));                       // grouped_xyz -= new_xyz (pointnet_util.py:42)
+                        if (p.g_shift) d[a] = __fsub_rn(d[a], __ldg(p.g_shift + q * 3 + a));  // -= shift_pred (model_rpointnet.py:56-57)
+                    }
+#pragma unroll
+                    for (int a = 0; a < 5; ++a)
+                        if (a < c) f[a] = __ldg(p.g_pts + (cloud * p.g_n + ii) * c + a);
+#pragma unroll
+                    for (int t2 = 0; t2 < 8; ++t2)  // columns [features(c) | dx dy dz | 0]; c is a runtime value <= 5
+                        v[t2] = (t2 < c) ? f[t2 < 5 ? t2 : 4] : (t2 == c ? d[0] : (t2 == c + 1 ? d[1] : (t2 == c + 2 ? d[2] : 0.f)));
+                }
+                uint4 pk = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                *reinterpret_cast<uint4 *>(stage + (r >> 3) * 1024 + (r & 7) * 128 + ((r & 7) << 4)) = pk;  // chunk 0 ^ (r & 7)
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full + 8 * s) : "memory");
+            if (++s == p.a_stages) { s = 0; par ^= 1; }
+        }
+    } else if (warp == p.epi_warps) {
         if (lane == 0) {
             int s = 0, par = 0, kb = 0;
             long t = blockIdx.x;
@@ -516,14 +565,14 @@ extern "C" int gspn_mlp_pack_weights(int cin, int cin_padded, int cout, const fl
 static long long *g_chain_prof = nullptr;  // tuning door: set by gspn_mlp_chain_set_profile, read at launch
 extern "C" void gspn_mlp_chain_set_profile(long long *prof5) { g_chain_prof = prof5; }
 
-extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a, const void *const *wimg, const float *const *scale,
-                              const float *const *shift, const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream) {
+static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, const void *a, const void *const *wimg,
+                        const float *const *scale, const float *const *shift, const int *relu, int pool, float *out_f32, void *out_bf16,
+                        gspn_stream_t stream) {
     GSPN_REQUIRE(rows >= 0 && nlayers >= 1 && nlayers <= kMaxLayers && pool >= 1);
     GSPN_REQUIRE_PTR(dims); GSPN_REQUIRE_PTR(wimg); GSPN_REQUIRE_PTR(scale); GSPN_REQUIRE_PTR(shift); GSPN_REQUIRE_PTR(relu);
     if (rows == 0) return GSPN_OK;
-    GSPN_REQUIRE_PTR(a);
+    if (a == nullptr && p.g_idx == nullptr) return GSPN_E_NULL_PTR;
     if (out_f32 == nullptr && out_bf16 == nullptr) return GSPN_E_NULL_PTR;
-    ChainParams p = {};
     p.rows = rows;
     p.ntiles = ceil_div_l(rows, kTileRows);
     p.nlayers = nlayers;
@@ -606,6 +655,28 @@ extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const voi
     if (p.epi_warps == 4) mlp_chain_kernel<4><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p);
     else mlp_chain_kernel<8><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p);
     return check_launch();
+}
+
+extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a, const void *const *wimg, const float *const *scale,
+                              const float *const *shift, const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream) {
+    ChainParams p = {};
+    return chain_launch(p, rows, nlayers, dims, a, wimg, scale, shift, relu, pool, out_f32, out_bf16, stream);
+}
+
+extern "C" int gspn_mlp_chain_gather(int b, int n, int m, int nsample, int c, const float *xyz, const float *new_xyz, const float *shift_pred,
+                                     const float *points, const int *idx, int nlayers, const int *dims, const void *const *wimg,
+                                     const float *const *scale, const float *const *shift, const int *relu, int pool, float *out_f32,
+                                     void *out_bf16, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && nsample > 0 && c >= 0);
+    if (c + 3 > 8) return GSPN_E_UNSUPPORTED;  // one 16-byte chunk per row; wider rows go through the tile image
+    if (b == 0 || m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(xyz); GSPN_REQUIRE_PTR(new_xyz); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(dims);
+    if (c > 0) GSPN_REQUIRE_PTR(points);
+    GSPN_REQUIRE(dims[0] == 64);
+    ChainParams p = {};
+    p.g_idx = idx; p.g_xyz = xyz; p.g_ctr = new_xyz; p.g_shift = shift_pred; p.g_pts = points;
+    p.g_n = n; p.g_m = m; p.g_k = nsample; p.g_c = c;
+    return chain_launch(p, (long)b * m * nsample, nlayers, dims, nullptr, wimg, scale, shift, relu, pool, out_f32, out_bf16, stream);
 }
 
 extern "C" int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float *points1, const float *points2, const int *idx,

@@ -76,6 +76,46 @@ def mlp_chain(a_img, rows, k0, layers, first_perm, pool, want_bf16=False):
     return out, out_h
 
 
+def mlp_chain_gather(xyz, new_xyz, shift, points, idx, layers, first_perm, pool):
+    """Layer chain whose first operand is gathered in-kernel from the ball-query indices (c+3 <= 8): no grouped tensor
+    in HBM.  Returns out_f32 (b*m*nsample/pool, cout)."""
+    from .pointnet_util import fold_layer
+    L = _lib.lib()
+    n_layers = len(layers)
+    b, n, _ = xyz.shape
+    _, m, k = idx.shape
+    c = 0 if points is None else points.shape[2]
+    dims = [64] + [l["weights"].shape[1] for l in layers]
+    imgs, scales, shifts = [], [], []
+    for i, layer in enumerate(layers):
+        kp = 64 if i == 0 else _pad64(dims[i])
+        imgs.append(_packed(layer, kp, first_perm if i == 0 else None, tag="first" if i == 0 else "w"))
+        sc, sh = fold_layer(layer)
+        scales.append(sc)
+        shifts.append(sh)
+    rows = b * m * k
+    out = torch.empty((rows // pool, dims[-1]), dtype=torch.float32, device=xyz.device)
+    arr_i = (ctypes.c_int * (n_layers + 1))(*dims)
+    arr_w = (ctypes.c_void_p * n_layers)(*[t.data_ptr() for t in imgs])
+    arr_s = (ctypes.c_void_p * n_layers)(*[t.data_ptr() for t in scales])
+    arr_b = (ctypes.c_void_p * n_layers)(*[t.data_ptr() for t in shifts])
+    arr_r = (ctypes.c_int * n_layers)(*([1] * n_layers))
+    check(L.gspn_mlp_chain_gather(b, n, m, k, c, xyz.data_ptr(), new_xyz.data_ptr(), None if shift is None else shift.data_ptr(),
+                                  None if points is None else points.data_ptr(), idx.data_ptr(), n_layers,
+                                  ctypes.cast(arr_i, ctypes.c_void_p), ctypes.cast(arr_w, ctypes.c_void_p), ctypes.cast(arr_s, ctypes.c_void_p),
+                                  ctypes.cast(arr_b, ctypes.c_void_p), ctypes.cast(arr_r, ctypes.c_void_p), pool, out.data_ptr(), None,
+                                  _stream()), "mlp_chain_gather")
+    return out
+
+
+GATHER_IN_CHAIN = True  # narrow rows (c+3 <= 8): build the first operand inside the chain kernel instead of a tile image
+
+
+def gather_ok(points):
+    c = 0 if points is None else points.shape[2]
+    return GATHER_IN_CHAIN and c + 3 <= 8 and (points is None or points.dtype == torch.float32)
+
+
 def tc_supported(layers, pool):
     if not (1 <= len(layers) <= MAX_LAYERS):
         return False
@@ -97,8 +137,10 @@ def sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz, sto
         with _stage(timers, scope + ":mlp"):
             first = _features_first(layers[0], c, use_xyz, points is not None)
             return idx, _run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
-    with _stage(timers, scope + ":ballquery_group"):
-        idx, _, img, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.bfloat16)
+    ld = 64 if gather_ok(points) else None
+    if ld is None:
+        with _stage(timers, scope + ":ballquery_group"):
+            idx, _, img, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.bfloat16)
     # tile-image columns are [features(c) | xyz(3) | 0]; the reference's kernel rows are [xyz | features]
     if points is None:
         perm = [0, 1, 2] + [-1] * (ld - 3)
@@ -106,6 +148,12 @@ def sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz, sto
         perm = [3 + k for k in range(c)] + [0, 1, 2] + [-1] * (ld - c - 3)
     else:
         perm = list(range(c)) + [-1] * (ld - c)
+    if gather_ok(points):
+        with _stage(timers, scope + ":ballquery_group"):
+            idx, _ = ops.query_ball_point(radius, nsample, xyz, new_xyz)
+        with _stage(timers, scope + ":mlp"):
+            pts = None if points is None else points.contiguous()
+            return idx, mlp_chain_gather(xyz.contiguous(), new_xyz.contiguous(), None, pts, idx, layers, perm, nsample)
     with _stage(timers, scope + ":mlp"):
         out, _ = mlp_chain(img, rows, ld, layers, perm, nsample)
     return idx, out

@@ -177,6 +177,14 @@ int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a,
                    const void *const *wimg, const float *const *scale, const float *const *shift,
                    const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream);
 
+/* Same chain, but layer 0's operand rows [points[b,idx,:c] | xyz[b,idx]-new_xyz[b,j]-shift[b,j] | 0] (c+3 <= 8, dims[0]=64) are
+ * gathered by the kernel's producer warp straight from the ball-query indices idx (b,m,nsample): the grouped tensor of
+ * sample_and_group (utils/pointnet_util.py:40-48) is never written to HBM.  Same values as gspn_ballquery_group + gspn_mlp_chain. */
+int gspn_mlp_chain_gather(int b, int n, int m, int nsample, int c, const float *xyz, const float *new_xyz, const float *shift_pred,
+                          const float *points, const int *idx, int nlayers, const int *dims, const void *const *wimg,
+                          const float *const *scale, const float *const *shift, const int *relu, int pool,
+                          float *out_f32, void *out_bf16, gspn_stream_t stream);
+
 /* ---- training form of the shared MLP (fp32): conv 1x1 + bias -> batch norm over the BATCH moments
  * (tf.contrib.layers.batch_norm, is_training=True, utils/tf_util.py:515-534) -> ReLU -> reduce_max, and its backward.
  * The GEMMs are gspn_mlp_layer_f32 (forward: scale=1, shift=bias, relu=0; dX: the same with W^T). */

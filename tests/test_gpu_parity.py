@@ -756,3 +756,24 @@ def test_fp_module_training_forward_backward(cuda, oracle):
     for a, b_ in zip(mine, ref):
         for key in ("weights", "biases", "gamma", "beta"):
             np.testing.assert_allclose(N(a[key].grad), N(b_[key].grad), rtol=2e-3, atol=5e-4, err_msg=key)
+
+
+def test_gather_in_chain_equals_tile_image_path(cuda):
+    """The chain that gathers its first operand from the indices gives bit-identical results to image + chain."""
+    from gspn_b200 import mlp_tc
+    rng = np.random.RandomState(4)
+    xyz, col = scenes.scannet_like_batch(110, 2, 4096)
+    for pts, k in ((col, 32), (None, 32), (col, 256)):
+        cin = 3 + (0 if pts is None else 3)
+        layers = rand_layers(rng, cin, [32, 64])
+        st = to_store(layers, "g/conv", cuda)
+        st["g/conv_post_"] = []
+        args = (T(xyz, cuda), None if pts is None else T(pts, cuda), 64, 0.5, k, [32, 64], None, False, False, None, "g")
+        assert mlp_tc.GATHER_IN_CHAIN
+        a = gspn_b200.pointnet_sa_module(*args, variables=st, precision="bf16")
+        mlp_tc.GATHER_IN_CHAIN = False
+        try:
+            b_ = gspn_b200.pointnet_sa_module(*args, variables=st, precision="bf16")
+        finally:
+            mlp_tc.GATHER_IN_CHAIN = True
+        assert torch.equal(a[2], b_[2]) and torch.equal(a[1], b_[1])
