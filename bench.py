@@ -347,6 +347,10 @@ def main():
         return 0
 
     peaks = load_peaks()
+    try:  # DRAM bytes per launch from the committed ncu --set full capture of the same kernels (profiles/ncu_traffic.json)
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu_traffic = {}
     stage_ms = timers.avg_ms()
     costs = stage_costs(B, precision)
     kernels = {}
@@ -358,13 +362,14 @@ def main():
             ach, peak, unit = amount / (t_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
         else:
             ach, peak, unit = amount / (t_ms * 1e-3) / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
-        kernels[name] = {"ms": round(t_ms, 4), "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit, "frac": round(ach / peak, 5)}
+        kernels[name] = {"ms": round(t_ms, 4), "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit, "frac": round(ach / peak, 5),
+                         "algorithmic": amount, "traffic": ncu_traffic.get(name, {}).get("traffic_bytes")}
     dom = next(iter(kernels)) if kernels else None
     roofline = None
     if dom:
         k = kernels[dom]
         roofline = {"kernel": dom, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"], "frac": k["frac"],
-                    "traffic": None, "peak_source": peaks["source"],
+                    "traffic": k["traffic"], "algorithmic": k["algorithmic"], "peak_source": peaks["source"],
                     "measured": "eager in-order pass over the same K batches inside this run (graph replays cannot be bracketed by events)",
                     "note": "dominant stage by device time; FPS is a chain of m-1 dependent rounds (latency-bound), its HBM fraction is "
                             "reported because the contract asks for it, see DESIGN.md; per-stage rooflines in 'kernels'"}
