@@ -61,3 +61,23 @@ def test_ops_refuse_cpu_tensors():
         gspn_b200.farthest_point_sample(0, torch.zeros(1, 8, 3))
     with pytest.raises(ValueError, match="QueryBallPoint expects positive radius"):
         gspn_b200.query_ball_point(0.0, 4, torch.zeros(1, 8, 3), torch.zeros(1, 2, 3))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU / PyTorch fallback: without the CUDA library the product path raises instead of computing elsewhere."""
+    import pytest
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libgspn_b200.so"))
+    with pytest.raises(_lib.GspnError, match="no CPU/PyTorch fallback"):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under gspn_b200/ may import it."""
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "gspn_b200", "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert "import oracle" not in src and "from oracle" not in src, path
+    for path in glob.glob(os.path.join(ROOT, "gspn_b200", "csrc", "*")):
+        if os.path.isfile(path) and not path.endswith(".so"):
+            assert "oracle" not in open(path, errors="ignore").read().lower() or path.endswith(".log"), path
