@@ -85,6 +85,30 @@ __device__ __forceinline__ void f_mbar_wait(uint32_t bar, uint32_t parity) {
         "FD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two points per instruction, each half IEEE round-to-nearest,
+// so the per-point result is bit-identical to sqdist_fma
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 constexpr int kMaxWarps = 32;
 constexpr int kMaxCand = 128;  // CLUSTER * warps-per-CTA candidates per round in the all-to-all exchange
 
@@ -134,6 +158,9 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const float *p = xyz + (size_t)cloud * n * 3;
 
+    constexpr bool PACKED = (PPT % 2 == 0);
+    constexpr int NP = PACKED ? PPT / 2 : 1;
+    unsigned long long qx[NP], qy[NP], qz[NP];  // PACKED: the coordinates live as fp32x2 pairs (points 2i, 2i+1)
     float px[PPT], py[PPT], pz[PPT], td[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
@@ -146,6 +173,14 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
             td[j] = -1.0f;  // min(d,-1) = -1 never beats a real point (distances are >= 0)
         }
         sxyz[j * blockDim.x + threadIdx.x] = make_float4(px[j], py[j], pz[j], 0.f);  // read back by this thread only
+    }
+    if (PACKED) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            qx[i] = f2_pack(px[2 * i], px[2 * i + 1]);
+            qy[i] = f2_pack(py[2 * i], py[2 * i + 1]);
+            qz[i] = f2_pack(pz[2 * i], pz[2 * i + 1]);
+        }
     }
     float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
     if (gtid == 0) out[(size_t)cloud * m] = 0;
@@ -169,10 +204,25 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         if (CLUSTER > 1 && threadIdx.x == 0)  // this round's phase completes after ncand x (16+4) bytes have landed
             f_mbar_expect_tx(f_smem_u32(&xbar[par]), (uint32_t)ncand * 20u);
         if (PROFILE) t0 = clock64();
+        if (PACKED) {
+            const unsigned long long xx = f2_pack(x1, x1), yy = f2_pack(y1, y1), zz = f2_pack(z1, z1);
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-            float d = sqdist_fma(px[j], py[j], pz[j], x1, y1, z1);
-            td[j] = fminf(d, td[j]);
+            for (int i = 0; i < NP; ++i) {
+                const unsigned long long dx = f2_sub(qx[i], xx), dy = f2_sub(qy[i], yy), dz = f2_sub(qz[i], zz);
+                unsigned long long t = f2_mul(dy, dy);  // same order as the reference's compiled code: dy*dy, fma dx, fma dz
+                t = f2_fma(dx, dx, t);
+                t = f2_fma(dz, dz, t);
+                float d0, d1;
+                f2_unpack(t, d0, d1);
+                td[2 * i] = fminf(d0, td[2 * i]);
+                td[2 * i + 1] = fminf(d1, td[2 * i + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                float d = sqdist_fma(px[j], py[j], pz[j], x1, y1, z1);
+                td[j] = fminf(d, td[j]);
+            }
         }
         float best;
         int bj;
