@@ -413,13 +413,50 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
                         }
                     }
                 } else {
-                    // max over the 32 rows this warp holds: ReLU output is >= 0, so float order == int order
-                    int keep = 0;
+                    // max over the 32 rows this warp holds, for 32 columns at once: recursive halving -- at step h a lane
+                    // keeps the half of its columns selected by its lane bit and takes the partner's values for them
+                    // (31 SHFL + 31 FMNMX instead of 32 warp-wide redux); lane L ends with the max of column L
+                    float w16[16], w8[8], w4[4], w2[2];
+                    {
+                        const bool up = lane & 16;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        int mx = __reduce_max_sync(GSPN_FULL_MASK, __float_as_int(f[i]));
-                        if (lane == i) keep = mx;
+                        for (int i = 0; i < 16; ++i) {
+                            float send = up ? f[i] : f[i + 16], keepv = up ? f[i + 16] : f[i];
+                            w16[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 16));
+                        }
                     }
+                    {
+                        const bool up = lane & 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float send = up ? w16[i] : w16[i + 8], keepv = up ? w16[i + 8] : w16[i];
+                            w8[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 8));
+                        }
+                    }
+                    {
+                        const bool up = lane & 4;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float send = up ? w8[i] : w8[i + 4], keepv = up ? w8[i + 4] : w8[i];
+                            w4[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 4));
+                        }
+                    }
+                    {
+                        const bool up = lane & 2;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float send = up ? w4[i] : w4[i + 2], keepv = up ? w4[i + 2] : w4[i];
+                            w2[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 2));
+                        }
+                    }
+                    float pooled;
+                    {
+                        const bool up = lane & 1;
+                        float send = up ? w2[0] : w2[1], keepv = up ? w2[1] : w2[0];
+                        pooled = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 1));
+                    }
+                    // lane L now holds column (L&16) + (L&8) + (L&4) + (L&2) + (L&1) == L of this 32-column chunk
+                    const int keep = __float_as_int(pooled);
                     const long row0 = tile * kTileRows + quad * 32;
                     if (row0 < p.rows) {
                         const long grp = row0 / p.pool;
