@@ -336,6 +336,82 @@ __global__ void __launch_bounds__(1024, 1) fps_stream_kernel(int n, int m, const
     }
 }
 
+// Data-prep sized clouds (data_prep.py:65-91: 1e5-5e5 mesh vertices -> 30000 samples): a 16-CTA cluster of 1024 threads keeps the
+// running min-distances of up to 524288 points in registers (32 per thread); the coordinates (12 B/point, L2 resident) are
+// streamed every round, 1/16 of the cloud per SM.  Two-level reduce: warps -> CTA winner through shared memory, then the
+// 16 CTA winners all-to-all with st.async + mbarrier exactly like the resident kernel.
+constexpr int kBigCluster = 16, kBigThreads = 1024, kBigPPT = 32;
+__global__ void __launch_bounds__(kBigThreads, 1) fps_cluster_stream_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out) {
+    __shared__ Slot wslot[2][32];
+    __shared__ unsigned wkey[2][32];
+    __shared__ Slot cslot[2][32];
+    __shared__ unsigned ckey[2][32];
+    __shared__ __align__(8) uint64_t xbar[2];
+    const int cloud = blockIdx.y;
+    const unsigned rank = cg::this_cluster().block_rank();
+    const int T = kBigThreads * kBigCluster;  // multiple of 512: a thread's points share k mod 512, keys ascend with j
+    const int gtid = rank * kBigThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *p = xyz + (size_t)cloud * n * 3;
+    float td[kBigPPT];
+#pragma unroll
+    for (int j = 0; j < kBigPPT; ++j) td[j] = (gtid + j * T < n) ? 1e38f : -1.0f;
+    for (int i = threadIdx.x; i < 2 * 32; i += kBigThreads) {
+        (&wslot[0][0])[i] = Slot{0.f, 0.f, 0.f, __float_as_int(-1.0f)}; (&wkey[0][0])[i] = 0xFFFFFFFFu;
+        (&cslot[0][0])[i] = Slot{0.f, 0.f, 0.f, __float_as_int(-1.0f)}; (&ckey[0][0])[i] = 0xFFFFFFFFu;
+    }
+    if (threadIdx.x == 0) {
+        f_mbar_init(f_smem_u32(&xbar[0]), 1);
+        f_mbar_init(f_smem_u32(&xbar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);
+    if (gtid == 0) out[(size_t)cloud * m] = 0;
+    __syncthreads();
+    cluster_barrier();
+    for (int r = 1; r < m; ++r) {
+        const int par = r & 1;
+        if (threadIdx.x == 0) f_mbar_expect_tx(f_smem_u32(&xbar[par]), (uint32_t)kBigCluster * 20u);
+        float best = -1.0f, bx = 0.f, by = 0.f, bz = 0.f;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < kBigPPT; ++j) {
+            const int k = gtid + j * T;
+            if (k < n) {
+                const float x = __ldg(p + 3 * (size_t)k), y = __ldg(p + 3 * (size_t)k + 1), z = __ldg(p + 3 * (size_t)k + 2);
+                const float t = fminf(sqdist_fma(x, y, z, x1, y1, z1), td[j]);
+                td[j] = t;
+                if (t > best) { best = t; bj = j; bx = x; by = y; bz = z; }
+            }
+        }
+        Cand c;
+        c.dbits = __float_as_int(best); c.key = fps_key(gtid + bj * T); c.x = bx; c.y = by; c.z = bz;
+        c = warp_argmax(c);
+        if (lane == 0) { wslot[par][warp] = Slot{c.x, c.y, c.z, c.dbits}; wkey[par][warp] = c.key; }
+        __syncthreads();
+        if (warp == 0) {
+            Cand w;
+            Slot s0 = wslot[par][lane];
+            w.dbits = s0.dbits; w.key = wkey[par][lane]; w.x = s0.x; w.y = s0.y; w.z = s0.z;
+            w = warp_argmax(w);
+            if (lane < kBigCluster) {
+                const uint32_t rbar = map_to_rank(f_smem_u32(&xbar[par]), lane);
+                st_async_v4(map_to_rank(f_smem_u32(&cslot[par][rank]), lane), __float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z),
+                            (uint32_t)w.dbits, rbar);
+                st_async_b32(map_to_rank(f_smem_u32(&ckey[par][rank]), lane), w.key, rbar);
+            }
+        }
+        f_mbar_wait(f_smem_u32(&xbar[par]), (uint32_t)(((r - 1) >> 1) & 1));
+        Cand w;
+        Slot s0 = cslot[par][lane];
+        w.dbits = s0.dbits; w.key = ckey[par][lane]; w.x = s0.x; w.y = s0.y; w.z = s0.z;
+        c = warp_argmax(w);
+        x1 = c.x; y1 = c.y; z1 = c.z;
+        if (gtid == 0) out[(size_t)cloud * m + r] = fps_unkey(c.key);
+    }
+    cluster_barrier();
+}
+
 template <int PPT, int CLUSTER, int MAXT, bool PROFILE, int CPL>
 static int launch_resident_cpl(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s, long long *prof) {
     auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT, PROFILE, CPL>;
@@ -413,6 +489,7 @@ static void choose_cfg(int n, int *threads, int *ppt, int *cluster) {
 }
 
 constexpr int kMaxResident = 512 * 16 * 16;
+constexpr int kMaxClusterStream = kBigCluster * kBigThreads * kBigPPT;  // 524288
 
 }  // namespace gspn
 
@@ -440,7 +517,7 @@ extern "C" int gspn_fps_max_resident_points(void) { return kMaxResident; }
 
 extern "C" size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m) {
     (void)m;
-    if (n <= kMaxResident || b <= 0) return 0;
+    if (n <= kMaxClusterStream || b <= 0) return 0;
     return sizeof(float) * (size_t)b * (size_t)n;
 }
 
@@ -471,6 +548,19 @@ extern "C" int gspn_farthest_point_sample(int b, int n, int m, const float *inp,
     if (b == 0) return GSPN_OK;
     GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out);
     if (n <= kMaxResident) return gspn_farthest_point_sample_cfg(b, n, m, inp, out, 0, 0, 0, stream);
+    if (n <= kMaxClusterStream && b <= 65535) {
+        GSPN_CUDA_OK(cudaFuncSetAttribute(fps_cluster_stream_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kBigCluster, b, 1);
+        cfg.blockDim = dim3(kBigThreads, 1, 1);
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kBigCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, fps_cluster_stream_kernel, n, m, inp, out));
+        return check_launch();
+    }
     size_t need = gspn_farthest_point_sample_workspace_bytes(b, n, m);
     if (workspace == nullptr || workspace_bytes < need) return GSPN_E_WORKSPACE;
     fps_stream_kernel<<<b, 1024, 0, as_stream(stream)>>>(n, m, inp, (float *)workspace, out);

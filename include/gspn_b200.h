@@ -57,8 +57,9 @@ const char *gspn_last_cuda_error(void);
  *   farthestpointsamplingLauncher(b,n,m,inp,temp,out)  tf_sampling_g.cu:203
  * inp (b,n,3) f32 -> out (b,m) i32, bit-identical to the reference kernel
  * (out[:,0]=0; ties -> lowest (k mod 512, k)).  The reference's temp (32,n)
- * scratch is not needed when n <= gspn_fps_max_resident_points(); above that
- * pass workspace of gspn_farthest_point_sample_workspace_bytes(b,n,m). */
+ * scratch is not needed: clouds up to gspn_fps_max_resident_points() (131072) live entirely in registers, up to
+ * 524288 points a 16-CTA cluster keeps the distances in registers and streams coordinates from L2; only above that
+ * pass workspace of gspn_farthest_point_sample_workspace_bytes(b,n,m) for the single-CTA fallback. */
 size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m);
 int gspn_fps_max_resident_points(void);
 int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out,

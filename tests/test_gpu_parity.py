@@ -89,11 +89,12 @@ def test_fps_full_size_config2(cuda, oracle):
     assert all(a >= b * (1 - 1e-6) for a, b in zip(sel, sel[1:]))
 
 
-def test_fps_streaming_fallback_large_cloud(cuda, oracle):
-    n = gspn_b200._lib.lib().gspn_fps_max_resident_points() + 1000
-    xyz = scenes.uniform_cube(1, n, seed=12)
-    got = N(gspn_b200.farthest_point_sample(40, T(xyz, cuda)))
-    assert np.array_equal(got, oracle.farthest_point_sample(40, xyz))
+@pytest.mark.parametrize("n,m", [(131072 + 1000, 40), (300000, 64), (524288 + 7, 24)])
+def test_fps_data_prep_sized_clouds(cuda, oracle, n, m):
+    """Above the register-resident limit: 16-CTA cluster streaming kernel (<= 524288 points), then the single-CTA fallback."""
+    xyz = scenes.with_duplicates(scenes.uniform_cube(1, n, seed=12), 0.05)
+    got = N(gspn_b200.farthest_point_sample(m, T(xyz, cuda)))
+    assert np.array_equal(got, oracle.farthest_point_sample(m, xyz))
 
 
 # ------------------------------------------------------------------------------------ gather / group
