@@ -239,7 +239,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--scenes-per-gpu", type=int, default=SCENES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--depth", type=int, default=6, help="batches kept in flight (CUDA-graph lanes on separate streams)")
+    ap.add_argument("--depth", type=int, default=8, help="batches kept in flight (CUDA-graph lanes on separate streams)")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--e2e-fp32", action="store_true", help="e2e leg downloads the fp32 copy of the feature map (PCIe-bound)")
     args = ap.parse_args()

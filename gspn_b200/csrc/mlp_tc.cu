@@ -16,6 +16,7 @@
 //   * epilogue: tcgen05.ld 32x32b.x32 -> fp32 scale/shift (bias+BN folded) + ReLU -> bf16 ->
 //     swizzled st.shared (next layer's A) ; last layer: max over the nsample rows of a group with
 //     redux.sync on the (non-negative) float bits, coalesced fp32 / bf16 stores.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gspn {
@@ -689,6 +690,10 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
     // one CTA per SM (shared-memory bound): give it 8 epilogue warps; two CTAs per SM: 4 each (register file)
     p.epi_warps = occ >= 2 ? 4 : 8;
+    if (const char *e = getenv("GSPN_TC_EPI")) {  // tuning door
+        int v = atoi(e);
+        if (v == 4 || v == 8) p.epi_warps = v;
+    }
     if (p.epi_warps == 4) mlp_chain_kernel<4><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p);
     else mlp_chain_kernel<8><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p);
     return check_launch();
