@@ -1,5 +1,7 @@
 // ballquery_group.cu -- query_ball_point (tf_grouping_g.cu:6-39) and the fused
-// ball-query + group_point of sample_and_group (utils/pointnet_util.py:40-48).
+// ball-query + group_point of sample_and_group (utils/pointnet_util.py:40-48): the ordered-scan kernel used for
+// clouds below 4096 points (and whenever the caller gives no workspace); larger clouds go through the exact
+// uniform-grid search in grid_search.cu, which shares the row writer (group_rows.cuh) and the entry points below.
 //
 // Reference: one CTA per cloud, one thread per query, each thread streams all n points from
 // global memory with a divergent early exit; then a second kernel copies rows one scalar at a

@@ -5,12 +5,14 @@
 // past the first 3072 from global memory each round and reduces with a 9-step __syncthreads tree
 // on one CTA per cloud.  FPS is a chain of m-1 strictly sequential rounds, so what matters is the
 // latency of ONE round, not bandwidth.  Here a cloud is owned by a thread-block CLUSTER:
-//   * every thread keeps its PPT points (x,y,z) AND their running min-distance in registers for
-//     the whole kernel -- global memory is touched once (prologue) and for the m index stores;
-//   * per round: PPT fused distance updates, a thread-local argmax, two redux.sync per warp
-//     (max of the distance bits, then min of the tie-break key), one shared-memory hop per CTA,
-//     and one DSMEM all-to-all of the CTA winners (coordinates travel with the candidate, so the
-//     next round starts without a global load), closed by a cluster barrier.
+//   * every thread keeps its PPT points (x,y,z, packed as fp32x2 pairs) AND their running min-distance in
+//     registers for the whole kernel -- global memory is touched once (prologue) and for the m index stores;
+//   * per round: PPT/2 packed distance updates (FADD2/FMUL2/FFMA2), a tournament argmax, two redux.sync per
+//     warp (max of the distance bits, then min of the tie-break key), then a DSMEM all-to-all: every warp's
+//     winner (coordinates travel with the candidate, so the next round starts without a memory load) is pushed
+//     into every CTA's candidate table with st.async + mbarrier complete_tx; each CTA waits on its own
+//     mbarrier (double-buffered by round parity) and every warp reduces the table with one more warp argmax.
+//     No __syncthreads, no cluster barrier, no gpu-scope fence on the round path.
 //
 // Bit-exactness with the reference: distances use its compiled rounding (common.cuh sqdist_fma);
 // its winner among equal maxima is the lowest (k mod 512, k) -- thread-strided scan with strict '>'

@@ -5,17 +5,20 @@
 //
 //   * A operand (activations): 128 rows x K bf16, K-major, SWIZZLE_128B.  Layer 0 reads the tile image
 //     written by the fused ball-query+group kernel (or gspn_fp_assemble) -- each 128x64 block is one
-//     16 KiB cp.async.bulk (TMA bulk engine), no tensor map.  Layers >0 read what the previous
-//     layer's epilogue wrote into shared memory in the same swizzled layout.
+//     16 KiB cp.async.bulk (TMA bulk engine), no tensor map -- or, for rows of <= 8 columns, builds the
+//     tile in shared memory itself from the ball-query indices (gather mode).  Layers >0 read what the
+//     previous layer's epilogue wrote into shared memory in the same swizzled layout.
 //   * B operand (weights): W^T as [cout x cin] bf16 K-major blocks, pre-swizzled once by
-//     gspn_mlp_pack_weights, streamed through a 4-stage shared-memory ring by cp.async.bulk with
+//     gspn_mlp_pack_weights, streamed through a shared-memory ring by cp.async.bulk with
 //     mbarrier complete_tx; the ring runs ahead across layers and tiles.
 //   * D accumulates in TMEM (fp32, 128 lanes x cout columns); tcgen05.mma kind::f16, M=128,
-//     N<=128 per instruction, issued by one thread; tcgen05.commit releases ring stages and signals
-//     the epilogue.
-//   * epilogue: tcgen05.ld 32x32b.x32 -> fp32 scale/shift (bias+BN folded) + ReLU -> bf16 ->
-//     swizzled st.shared (next layer's A) ; last layer: max over the nsample rows of a group with
-//     redux.sync on the (non-negative) float bits, coalesced fp32 / bf16 stores.
+//     N<=128 per instruction; tcgen05.commit releases ring stages and signals the epilogue.
+//   * warp roles: 4 or 8 epilogue warps, an input-producer warp, a weight-producer warp and a CONVERGED
+//     MMA-issuer warp (elect.sync around tcgen05.mma only), handing tiles back and forth through the
+//     mma_done / epi_done mbarriers.
+//   * epilogue: software-pipelined tcgen05.ld 32x32b.x32 -> fp32 scale/shift (bias+BN folded) + ReLU
+//     -> bf16 -> swizzled st.shared (next layer's A); last layer: max over the nsample rows of a group by
+//     recursive-halving shuffles, or a smem-transposed coalesced fp32 store.
 #include <cstdlib>
 #include "common.cuh"
 
