@@ -45,7 +45,6 @@ def load_peaks():
 def _oracle_scene(scene_id):
     """One 32768-pt scene through the whole backbone on ONE host core with the CPU oracle
     (three_nn / three_interpolate / MLP in the reference's own rounding; see oracle/)."""
-    import numpy as np  # noqa: F401
     from oracle import oracle as O
     from gspn_b200 import backbone, scenes
     xyz, col = scenes.scannet_like_batch(scene_id, 1, NPOINTS)
@@ -247,7 +246,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from gspn_b200 import _lib, backbone, scenes

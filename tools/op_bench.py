@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gspn_b200 import _lib, backbone, mlp_tc, ops, scenes  # noqa: E402
+from gspn_b200 import backbone, mlp_tc, ops, scenes  # noqa: E402
 from gspn_b200 import pointnet_util as pu  # noqa: E402
 
 dev = torch.device("cuda:0")

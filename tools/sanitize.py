@@ -1,7 +1,7 @@
 """Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck / synccheck).
    compute-sanitizer --tool memcheck python tools/sanitize.py"""
 import os, sys
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gspn_b200
 from gspn_b200 import backbone, context_encoder, scenes
