@@ -41,6 +41,29 @@ __device__ __forceinline__ float sqdist_nofma(float ax, float ay, float az, floa
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Division by a runtime constant for values below 2^31: q = umulhi(x, mul) >> shr (round-up magic number, exact for
+// 0 <= x < 2^31 and 1 <= d < 2^31).  Element-indexed kernels use it instead of a 64-bit divide per element.
+struct FastDiv {
+    uint32_t d, mul, shr;
+    FastDiv() : d(1), mul(0), shr(0) {}
+    explicit FastDiv(uint32_t den) : d(den), mul(0), shr(0) {
+        if (den > 1) {
+            uint32_t lg = 0;
+            while ((1ull << lg) < den) ++lg;  // ceil(log2(den))
+            const unsigned long long pw = 1ull << (31 + lg);
+            mul = (uint32_t)((pw + den - 1) / den);
+            shr = lg - 1;
+        }
+    }
+    __host__ __device__ __forceinline__ uint32_t div(uint32_t x) const {
+#ifdef __CUDA_ARCH__
+        return d == 1 ? x : (__umulhi(x, mul) >> shr);
+#else
+        return d == 1 ? x : (uint32_t)(((unsigned long long)x * mul) >> 32) >> shr;
+#endif
+    }
+};
+
 __host__ __device__ inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -40,12 +40,14 @@ struct ChainParams {
     const unsigned char *a;
     int pool;
     float *out_f32;
+    int out_f32_vec;  // out_f32 is 32-byte aligned: 256-bit stores
     __nv_bfloat16 *out_bf16;
     int nch;  // weight rows (output channels) per ring stage / per MMA
     int tmem_cols;
     int epi_warps;           // 4, or 8 (two warps per TMEM lane quadrant, each taking half the columns)
     int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
-    uint32_t r0_bytes, r1_bytes, stage_bytes;
+    uint32_t r_bytes, stage_bytes;  // r_bytes: the activation region (hidden layers are written in place, see below)
+    uint32_t affine_off;            // byte offset of the folded scale/shift table
     long long *prof;  // optional: per-phase cycle counters of CTA 0 / thread 0 (tools/tc_profile.py)
     // gather mode (a == nullptr): layer 0's operand rows [features(c) | xyz - centre - shift | 0] (c+3 <= 8, K0 = 64) are built
     // in shared memory by the input-producer warp straight from the ball-query indices -- no tile image in HBM at all
@@ -71,6 +73,22 @@ __device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
         "@p bra D_%=;\n\t"
         "bra W_%=;\n\t"
         "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// Producer-side wait (ring slot free): not latency-critical, so back off between polls instead of competing with the
+// epilogue warps of the same SM sub-partition for issue slots (try_wait returns within a few cycles when it fails).
+__device__ __forceinline__ void mb_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(100);
+    }
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
@@ -126,6 +144,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+// {lo = bf16(max(a,0)), hi = bf16(max(b,0))} in one instruction (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+// one 256-bit global store (STG.E.256): 8 consecutive floats, 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float *dst, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 
 struct Cursor {  // position in the per-tile weight block sequence: layer, k-block, n-chunk (fastest)
     int l, kb, nc;
@@ -153,14 +183,12 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
     const uint32_t raw = s_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1024-byte aligned
     unsigned char *sm = smem_raw + (base - raw);
-    // layer l>0 reads R[(l-1)&1]; layer l (not last) writes R[l&1]
-    const uint32_t R[2] = {base, base + p.r0_bytes};
-    unsigned char *Rg[2] = {sm, sm + p.r0_bytes};
-    const uint32_t aring = base + p.r0_bytes + p.r1_bytes;
+    // ONE activation region, written in place: layer l>0 reads it as its A operand, and the epilogue of layer l only
+    // starts after every MMA of layer l has completed (mma_done), so it may overwrite that operand with layer l's output.
+    const uint32_t Rs = base;
+    const uint32_t aring = base + p.r_bytes;
     const uint32_t wring = aring + (uint32_t)p.a_stages * kTileBytes;
-    float *xpose = reinterpret_cast<float *>(sm + p.r0_bytes + p.r1_bytes + (size_t)p.a_stages * kTileBytes +
-                                             (size_t)p.w_stages * p.stage_bytes);  // [4 warps][32][33] output transpose pad
-    float *affine = xpose + (p.pool == 1 ? p.epi_warps * 32 * 33 : 0);  // 32*33*4 bytes per pad keeps 16-byte alignment
+    float *affine = reinterpret_cast<float *>(sm + p.affine_off);
     const uint32_t w_full = s_u32(&bars[0]), w_empty = s_u32(&bars[kMaxStages]), a_full = s_u32(&bars[2 * kMaxStages]),
                    a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]),
                    epi_done = s_u32(&bars[4 * kMaxStages + 1]);
@@ -171,11 +199,9 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
-    int aoff[kMaxLayers];
     {
         int o = 0;
         for (int l = 0; l < p.nlayers; ++l) {
-            aoff[l] = o;
             for (int i = tid; i < p.N[l]; i += blockDim.x) {
                 affine[o + i] = __ldg(p.scale[l] + i);
                 affine[o + p.N[l] + i] = __ldg(p.shift[l] + i);
@@ -188,7 +214,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
         uint4 z = make_uint4(0, 0, 0, 0);
         uint4 *r = reinterpret_cast<uint4 *>(sm);
         // gather mode also zeroes the input ring: each row only ever writes its first 16-byte chunk
-        const uint32_t zbytes = p.r0_bytes + p.r1_bytes + (p.a ? 0u : (uint32_t)p.a_stages * kTileBytes);
+        const uint32_t zbytes = p.r_bytes + (p.a ? 0u : (uint32_t)p.a_stages * kTileBytes);
         for (uint32_t i = tid; i < zbytes / 16; i += blockDim.x) r[i] = z;
     }
     if (warp == 0) {
@@ -215,8 +241,8 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
         const int c = p.g_c;
         long t = blockIdx.x;
         for (int i = 0; i < total_a; ++i, t += gridDim.x) {
-            if (i >= p.a_stages) mb_wait(a_empty + 8 * s, (uint32_t)(par ^ 1));
-            unsigned char *stage = sm + p.r0_bytes + p.r1_bytes + (size_t)s * kTileBytes;
+            if (i >= p.a_stages) mb_wait_relaxed(a_empty + 8 * s, (uint32_t)(par ^ 1));
+            unsigned char *stage = sm + p.r_bytes + (size_t)s * kTileBytes;
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 const int r = lane + 32 * rr;
@@ -253,7 +279,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             int s = 0, par = 0, kb = 0;
             long t = blockIdx.x;
             for (int i = 0; i < total_a; ++i) {
-                if (i >= p.a_stages) mb_wait(a_empty + 8 * s, (uint32_t)(par ^ 1));
+                if (i >= p.a_stages) mb_wait_relaxed(a_empty + 8 * s, (uint32_t)(par ^ 1));
                 mb_expect_tx(a_full + 8 * s, kTileBytes);
                 bulk_load(aring + s * kTileBytes, p.a + ((size_t)t * kb0 + kb) * kTileBytes, kTileBytes, a_full + 8 * s);
                 if (++kb == kb0) { kb = 0; t += gridDim.x; }
@@ -265,7 +291,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             int s = 0, par = 0;
             Cursor wc = {0, 0, 0};
             for (int i = 0; i < total_w; ++i) {
-                if (i >= p.w_stages) mb_wait(w_empty + 8 * s, (uint32_t)(par ^ 1));
+                if (i >= p.w_stages) mb_wait_relaxed(w_empty + 8 * s, (uint32_t)(par ^ 1));
                 const int rows_i = min(p.nch, p.N[wc.l] - wc.nc * p.nch);
                 const uint32_t bytes = (uint32_t)rows_i * 128u;
                 mb_expect_tx(w_full + 8 * s, bytes);
@@ -290,6 +316,8 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
                     const int nchunks = (Nl + p.nch - 1) / p.nch;
                     // every operand wait that can be satisfied from what the rings already hold is done BEFORE the
                     // epilogue hand-off, so that after it the loop is  tcgen05.mma x4 + commit  per block
+                    long long mw0 = 0;
+                    if (p.prof) mw0 = clock64();
                     const int nblk = KBl * nchunks;
                     const int pre_w = nblk < p.w_stages ? nblk : p.w_stages;
                     const int pre_a = (l == 0) ? (KBl < p.a_stages ? KBl : p.a_stages) : 0;
@@ -303,11 +331,14 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
                     }
                     const int last_rows = Nl - (nchunks - 1) * p.nch;
                     const uint32_t idesc_full = instr_desc(128, p.nch), idesc_last = instr_desc(128, last_rows);
-                    const uint32_t a_base = (l == 0) ? 0u : R[(l - 1) & 1];
+                    const uint32_t a_base = (l == 0) ? 0u : Rs;
                     if (!first) { mb_wait(epi_done, epi_par); epi_par ^= 1; }  // TMEM drained, next A operand written
                     first = false;
                     long long mt0 = 0;
-                    if (p.prof) mt0 = clock64();
+                    if (p.prof) {
+                        mt0 = clock64();  // slot 7: operand pre-waits + epilogue hand-off, as seen by the issuer
+                        if (blockIdx.x == 0 && lane == 0) atomicAdd((unsigned long long *)p.prof + 7, (unsigned long long)(mt0 - mw0));
+                    }
                     tc_fence_after();
                     int blk = 0;
                     for (int kb = 0; kb < KBl; ++kb) {
@@ -324,10 +355,13 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
                             if (blk >= pre_w) { mb_wait(w_full + 8 * s, (uint32_t)wu_par); tc_fence_after(); }
                             const uint32_t idesc = (nc == nchunks - 1) ? idesc_last : idesc_full;
                             const uint64_t bd = smem_desc(wring + s * p.stage_bytes);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
-                                if (elect_one()) tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
-                            if (elect_one()) tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
+                                for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
+                                    tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                                tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
+                            }
+                            __syncwarp();
                             if (++wu_s == p.w_stages) { wu_s = 0; wu_par ^= 1; }
                         }
                         if (l == 0) {
@@ -352,6 +386,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
     uint32_t done_par = 0;
 
     for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        int ao = 0;  // running offset of layer l's [scale | shift] in the affine table
         for (int l = 0; l < p.nlayers; ++l) {
             const int Nl = p.N[l];
             long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
@@ -363,51 +398,65 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
 
             // ---- epilogue: thread = row (TMEM lane), 32 columns at a time
             const bool last = (l == p.nlayers - 1);
-            const float *sc = affine + aoff[l], *sh = sc + Nl;
+            const float *sc = affine + ao, *sh = sc + Nl;
+            ao += 2 * Nl;
             const int quad = warp & 3, half = warp >> 2, nhalf = p.epi_warps >> 2;
             const int row = quad * 32 + lane;
             const long grow = tile * kTileRows + row;
             const int c_lo = ((Nl >> 5) * half / nhalf) << 5, c_hi = ((Nl >> 5) * (half + 1) / nhalf) << 5;  // this warp's columns
-            unsigned char *outb = Rg[l & 1];
+            unsigned char *outb = sm;
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16);
+            const bool relu = p.relu[l] != 0;
             auto process = [&](const uint32_t (&v)[32], const int c0) {
                 float f[32];
                 {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
-                    const bool relu = p.relu[l] != 0;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const float4 a4 = sc4[g], b4 = sh4[g];  // same address in every lane: one broadcast LDS.128 each
-                        float x0 = fmaf(__uint_as_float(v[4 * g]), a4.x, b4.x), x1 = fmaf(__uint_as_float(v[4 * g + 1]), a4.y, b4.y);
-                        float x2 = fmaf(__uint_as_float(v[4 * g + 2]), a4.z, b4.z), x3 = fmaf(__uint_as_float(v[4 * g + 3]), a4.w, b4.w);
-                        f[4 * g] = relu ? fmaxf(x0, 0.f) : x0; f[4 * g + 1] = relu ? fmaxf(x1, 0.f) : x1;
-                        f[4 * g + 2] = relu ? fmaxf(x2, 0.f) : x2; f[4 * g + 3] = relu ? fmaxf(x3, 0.f) : x3;
+                        f[4 * g] = fmaf(__uint_as_float(v[4 * g]), a4.x, b4.x); f[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), a4.y, b4.y);
+                        f[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), a4.z, b4.z); f[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), a4.w, b4.w);
                     }
                 }
                 if (!last) {
+                    // ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32): no separate max per element
+                    unsigned char *dst = outb + (size_t)(c0 >> 6) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128;
+                    const int cc0 = (c0 >> 3) & 7;  // 16-byte chunk index inside the 64-column block: 0 or 4
+                    if (relu) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        int cc = (c0 >> 3) + g;  // 16-byte chunk index along K of the next layer
-                        uint4 pk = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
-                                              pack2(f[8 * g + 6], f[8 * g + 7]));
-                        *reinterpret_cast<uint4 *>(outb + (size_t)(cc >> 3) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128 +
-                                                   (((cc & 7) ^ (row & 7)) << 4)) = pk;
-                    }
-                } else if (p.pool == 1) {
-                    if (p.out_f32) {
-                        // thread = row here, but a row's 32 floats are what is contiguous in memory: transpose the
-                        // warp's 32x32 block through its private smem pad so every store instruction writes one full line
-                        float *tp = xpose + warp * (32 * 33);  // one pad per epilogue warp
-                        __syncwarp();
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 pk = make_uint4(pack2_relu(f[8 * g], f[8 * g + 1]), pack2_relu(f[8 * g + 2], f[8 * g + 3]),
+                                                  pack2_relu(f[8 * g + 4], f[8 * g + 5]), pack2_relu(f[8 * g + 6], f[8 * g + 7]));
+                            *reinterpret_cast<uint4 *>(dst + ((((cc0 + g)) ^ (row & 7)) << 4)) = pk;
+                        }
+                    } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = f[i];
-                        __syncwarp();
-                        const long r0 = tile * kTileRows + quad * 32;
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r)
-                            if (r0 + r < p.rows) __stcs(p.out_f32 + (r0 + r) * Nl + c0 + lane, tp[r * 33 + lane]);
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 pk = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                                  pack2(f[8 * g + 6], f[8 * g + 7]));
+                            *reinterpret_cast<uint4 *>(dst + ((((cc0 + g)) ^ (row & 7)) << 4)) = pk;
+                        }
                     }
+                    return;
+                }
+                if (relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
+                if (p.pool == 1) {
+                    // thread = row: its 32 columns are 128 contiguous bytes of the output row.  Four 256-bit stores (one full
+                    // 32-byte sector per lane each) instead of a shared-memory transpose: the epilogue is issue-bound
                     if (grow < p.rows) {
+                        if (p.out_f32) {
+                            float *o = p.out_f32 + grow * Nl + c0;
+                            if (p.out_f32_vec) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) st_global_v8(o + 8 * g, &f[8 * g]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) o[i] = f[i];
+                            }
+                        }
                         if (p.out_bf16) {
                             uint4 *o = reinterpret_cast<uint4 *>(p.out_bf16 + grow * Nl + c0);
 #pragma unroll
@@ -476,16 +525,38 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             // software-pipelined TMEM reads: the load of the next 32 columns is in flight while this one is processed
             {
                 uint32_t va[32], vb[32];
+                long long e0 = 0, e1 = 0, e2 = 0;
+                if (p.prof) e0 = clock64();
                 if (c_lo < c_hi) tc_ld32(tbase + c_lo, va);
                 for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
                     tc_wait_ld();
+                    if (p.prof && c0 == c_lo) e1 = clock64();
                     if (c0 + 32 < c_hi) tc_ld32(tbase + c0 + 32, vb);
                     process(va, c0);
+                    if (p.prof && c0 == c_lo) {
+                        e2 = clock64();
+                        if (blockIdx.x == 0 && tid == 0) {  // slots 8..10: first TMEM load latency, first chunk's processing, chunks
+                            atomicAdd((unsigned long long *)p.prof + 8, (unsigned long long)(e1 - e0));
+                            atomicAdd((unsigned long long *)p.prof + 9, (unsigned long long)(e2 - e1));
+                            atomicAdd((unsigned long long *)p.prof + 10, (unsigned long long)((c_hi - c_lo) >> 5));
+                        }
+                    }
                     if (c0 + 32 < c_hi) {
                         tc_wait_ld();
                         if (c0 + 64 < c_hi) tc_ld32(tbase + c0 + 64, va);
                         process(vb, c0 + 32);
                     }
+                }
+            }
+            // a hidden layer whose width is 32 mod 64 leaves the upper half of its last 64-column block to the K padding of
+            // the next layer: keep it zero (the region is reused in place, an earlier, wider layer may have written there)
+            if (!last && (Nl & 63) && half == 0) {
+                const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int cc = (Nl >> 3) + g;
+                    *reinterpret_cast<uint4 *>(outb + (size_t)(cc >> 3) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128 +
+                                               (((cc & 7) ^ (row & 7)) << 4)) = z;
                 }
             }
             if (p.prof) pt3 = clock64();
@@ -525,15 +596,23 @@ __global__ void pack_weights_kernel(int cin, int cin_padded, int cout, const flo
 // ---- FP front end: [three_interpolate(points2) | points1 | 0] -> bf16 tile image (one 16-byte chunk per thread)
 __global__ void __launch_bounds__(256) fp_assemble_kernel(long rows, int n, int m, int c1, int c2, const float *__restrict__ points1,
                                                           const float *__restrict__ points2, const int *__restrict__ idx,
-                                                          const float *__restrict__ weight, unsigned char *__restrict__ img, int ld) {
+                                                          const float *__restrict__ weight, unsigned char *__restrict__ img, int ld,
+                                                          const FastDiv div_chunks, const FastDiv div_n) {
     const int chunks = ld >> 3;
     const long total = rows * chunks;
+    const bool small = total < (1L << 31);  // element indices fit the multiply-shift divider
     const bool vec2 = (c2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(points2) & 15u) == 0);
     const bool vec1 = (c2 % 8 == 0) && (c1 % 4 == 0) && points1 && ((reinterpret_cast<uintptr_t>(points1) & 15u) == 0);
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-        long row = e / chunks;
+        long row, bi;
+        if (small) {
+            row = div_chunks.div((uint32_t)e);
+            bi = div_n.div((uint32_t)row);
+        } else {
+            row = e / chunks;
+            bi = row / n;
+        }
         int ch = (int)(e - row * chunks);
-        long bi = row / n;
         float v[8];
         const int col0 = ch * 8;
         if (col0 + 8 <= c2 && vec2) {
@@ -640,33 +719,48 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     p.prof = g_chain_prof;
     p.pool = pool;
     p.out_f32 = out_f32;
+    p.out_f32_vec = (reinterpret_cast<uintptr_t>(out_f32) & 31u) == 0;
     p.out_bf16 = (__nv_bfloat16 *)out_bf16;
     p.nch = maxn < 128 ? maxn : 128;
     p.tmem_cols = 32;
     while (p.tmem_cols < maxn) p.tmem_cols <<= 1;
-    // region l&1 holds the output of (non-last) layer l, i.e. the next layer's A operand
-    int rk[2] = {0, 0};
+    // the activation region holds the widest hidden layer (hidden layers are written in place)
+    int rk = 0;
     for (int l = 0; l + 1 < nlayers; ++l) {
         int kp = ((p.N[l] + 63) / 64) * 64;
-        rk[l & 1] = kp > rk[l & 1] ? kp : rk[l & 1];
+        rk = kp > rk ? kp : rk;
     }
-    p.r0_bytes = (uint32_t)(rk[0] / 64) * kTileBytes;
-    p.r1_bytes = (uint32_t)(rk[1] / 64) * kTileBytes;
+    p.r_bytes = (uint32_t)(rk / 64) * kTileBytes;
     p.stage_bytes = (uint32_t)p.nch * 128u;
-    // ring depths: the deepest rings that still give the best CTA co-residency (a second CTA on the SM overlaps
-    // its MMAs with this one's epilogue); TMEM (512 columns/SM) bounds co-residency too
+    // Shared-memory plan: [activation region | input ring | weight ring | affine table].
+    // Pick the deepest rings that still give the best CTA co-residency (a second CTA on the SM overlaps its MMAs with
+    // this one's epilogue); TMEM (512 columns/SM) and the register file bound co-residency too.
     const int occ_tmem = 512 / p.tmem_cols;
-    const size_t fixed = 1024 + (size_t)p.r0_bytes + p.r1_bytes + affine_floats * sizeof(float) + (pool == 1 ? (8 * 32 * 33) * sizeof(float) : 0);
+    int occ_cap = 2;  // 128 registers x 224 threads: two CTAs (plus an FPS CTA of another lane) fit the register file
+    if (const char *e = getenv("GSPN_TC_OCC")) {  // tuning door
+        int v = atoi(e);
+        if (v == 1 || v == 2) occ_cap = v;
+    }
     const int tries[4][2] = {{3, 4}, {2, 4}, {2, 3}, {2, 2}};
     size_t smem = 0;
     int occ = 0;
     for (int t = 0; t < 4; ++t) {
-        size_t sz = fixed + (size_t)tries[t][0] * kTileBytes + (size_t)tries[t][1] * p.stage_bytes;
+        const size_t rings = (size_t)p.r_bytes + (size_t)tries[t][0] * kTileBytes + (size_t)tries[t][1] * p.stage_bytes;
+        const size_t sz = 1024 + rings + affine_floats * sizeof(float);
         if (sz > 226 * 1024) continue;
         int o = (int)((228 * 1024) / (sz + 1024));
         o = o > occ_tmem ? occ_tmem : o;
-        o = o > 2 ? 2 : o;  // ~160 registers x 224 threads: two CTAs fill the register file
-        if (o > occ) { occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1]; }
+        o = o > occ_cap ? occ_cap : o;
+        if (o > occ) {
+            occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1];
+            p.affine_off = (uint32_t)rings;
+        }
+    }
+    // two CTAs x 4 epilogue warps per SM, or one CTA with 8 (168 registers x 352 threads fill the register file)
+    p.epi_warps = occ >= 2 ? 4 : 8;
+    if (const char *e = getenv("GSPN_TC_EPI")) {  // tuning door
+        int v = atoi(e);
+        if (v == 4 || v == 8) p.epi_warps = v;
     }
     if (occ < 1) return GSPN_E_UNSUPPORTED;
     // never let more CTAs co-reside than TMEM can serve: inflate the request if shared memory alone would allow it
@@ -691,12 +785,6 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     if (grid > p.ntiles) grid = p.ntiles;
     if (pool > 1 && pool != 32)
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
-    // one CTA per SM (shared-memory bound): give it 8 epilogue warps; two CTAs per SM: 4 each (register file)
-    p.epi_warps = occ >= 2 ? 4 : 8;
-    if (const char *e = getenv("GSPN_TC_EPI")) {  // tuning door
-        int v = atoi(e);
-        if (v == 4 || v == 8) p.epi_warps = v;
-    }
     if (p.epi_warps == 4) mlp_chain_kernel<4><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p);
     else mlp_chain_kernel<8><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p);
     return check_launch();
@@ -734,6 +822,7 @@ extern "C" int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float
     long total = rows * (ld / 8);
     long blk = ceil_div_l(total, 256);
     if (blk > 148L * 64) blk = 148L * 64;
-    fp_assemble_kernel<<<(unsigned)blk, 256, 0, as_stream(stream)>>>(rows, n, m, c1, c2, points1, points2, idx, weight, (unsigned char *)a_img, ld);
+    fp_assemble_kernel<<<(unsigned)blk, 256, 0, as_stream(stream)>>>(rows, n, m, c1, c2, points1, points2, idx, weight, (unsigned char *)a_img, ld,
+                                                                     FastDiv((uint32_t)(ld >> 3)), FastDiv((uint32_t)n));
     return check_launch();
 }
