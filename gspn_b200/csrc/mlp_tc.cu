@@ -20,6 +20,8 @@
 //     -> bf16 -> swizzled st.shared (next layer's A); last layer: max over the nsample rows of a group by
 //     recursive-halving shuffles, or a smem-transposed coalesced fp32 store.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link dependency)
 #include "common.cuh"
 
 namespace gspn {
@@ -48,6 +50,10 @@ struct ChainParams {
     int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
     uint32_t r_bytes, stage_bytes;  // r_bytes: the activation region (hidden layers are written in place, see below)
     uint32_t affine_off;            // byte offset of the folded scale/shift table
+    uint32_t stagger_ns;            // odd CTAs start this much later (pool == 1 chains with several tiles per CTA)
+    int tma_out;                    // pool == 1: output rows leave through per-warp swizzled staging + TMA tensor stores
+    uint32_t stage_off;             // byte offset of the staging area (kStageWarpBytes per epilogue warp)
+    int stage_alias;                // staging aliases the activation region (dead while the last layer's epilogue runs)
     long long *prof;  // optional: per-phase cycle counters of CTA 0 / thread 0 (tools/tc_profile.py)
     // gather mode (a == nullptr): layer 0's operand rows [features(c) | xyz - centre - shift | 0] (c+3 <= 8, K0 = 64) are built
     // in shared memory by the input-producer warp straight from the ball-query indices -- no tile image in HBM at all
@@ -95,6 +101,15 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  "r"(bar)
                  : "memory");
 }
+// TMA tensor store of one (32 rows x 32 columns) box from swizzled shared memory; coordinates are (column, row) elements
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src, int c0, int r0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(r0)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+constexpr int kStageWarpBytes = 6144;  // per epilogue warp: 32 rows x 128 B (f32, SWIZZLE_128B) + 32 rows x 64 B (bf16, SWIZZLE_64B)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -120,6 +135,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+template <int CW>
+__device__ __forceinline__ void tc_ld(uint32_t taddr, uint32_t (&v)[CW]) {
+    if constexpr (CW == 32) tc_ld32(taddr, v);
+    else tc_ld16(taddr, v);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -170,8 +198,11 @@ struct Cursor {  // position in the per-tile weight block sequence: layer, k-blo
     }
 };
 
-template <int EPI>  // epilogue warps: 4 (two CTAs per SM) or 8 (one CTA per SM)
-__global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_kernel(const ChainParams p) {
+// EPI epilogue warps (4: one per TMEM lane quadrant, 8: two per quadrant, each taking half the columns); MINB CTAs per SM
+// (register budget); CW columns per TMEM read (32, or 16 when 2 x 8 epilogue warps have to fit the register file)
+template <int EPI, int MINB, int CW>
+__global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const ChainParams p, const __grid_constant__ CUtensorMap tm_f32,
+                                                                        const __grid_constant__ CUtensorMap tm_bf16) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2];
@@ -227,6 +258,9 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
+    // de-phase the CTAs: all of them start together and run the same layer sequence, so without this every CTA reaches the
+    // output-writing last layer at the same time and the chip alternates between an HBM-write burst and HBM-idle compute
+    if (p.stagger_ns && (blockIdx.x & 1)) __nanosleep(p.stagger_ns);
     int blocks_per_tile = 0;
     for (int l = 0; l < p.nlayers; ++l) blocks_per_tile += ((p.N[l] + p.nch - 1) / p.nch) * (p.K[l] >> 6);
     const int kb0 = p.K[0] >> 6;
@@ -396,23 +430,29 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             tc_fence_after();
             if (p.prof) pt2 = clock64();
 
-            // ---- epilogue: thread = row (TMEM lane), 32 columns at a time
+            // ---- epilogue: thread = row (TMEM lane), CW columns at a time
             const bool last = (l == p.nlayers - 1);
+            if (p.tma_out && p.stage_alias && l == 0 && !last) {
+                // the staging boxes of the previous tile's output live in the activation region this epilogue is about to
+                // write: every warp's pending TMA stores must have finished READING shared memory first
+                if (lane == 0) bulk_wait_read0();
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI * 32) : "memory");
+            }
             const float *sc = affine + ao, *sh = sc + Nl;
             ao += 2 * Nl;
-            const int quad = warp & 3, half = warp >> 2, nhalf = p.epi_warps >> 2;
+            const int quad = warp & 3, half = warp >> 2, nhalf = EPI >> 2;
             const int row = quad * 32 + lane;
             const long grow = tile * kTileRows + row;
-            const int c_lo = ((Nl >> 5) * half / nhalf) << 5, c_hi = ((Nl >> 5) * (half + 1) / nhalf) << 5;  // this warp's columns
+            const int c_lo = ((Nl / CW) * half / nhalf) * CW, c_hi = ((Nl / CW) * (half + 1) / nhalf) * CW;  // this warp's columns
             unsigned char *outb = sm;
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16);
             const bool relu = p.relu[l] != 0;
-            auto process = [&](const uint32_t (&v)[32], const int c0) {
-                float f[32];
+            auto process = [&](const uint32_t (&v)[CW], const int c0) {
+                float f[CW];
                 {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
+                    for (int g = 0; g < CW / 4; ++g) {
                         const float4 a4 = sc4[g], b4 = sh4[g];  // same address in every lane: one broadcast LDS.128 each
                         f[4 * g] = fmaf(__uint_as_float(v[4 * g]), a4.x, b4.x); f[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), a4.y, b4.y);
                         f[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), a4.z, b4.z); f[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), a4.w, b4.w);
@@ -421,130 +461,130 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
                 if (!last) {
                     // ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32): no separate max per element
                     unsigned char *dst = outb + (size_t)(c0 >> 6) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128;
-                    const int cc0 = (c0 >> 3) & 7;  // 16-byte chunk index inside the 64-column block: 0 or 4
+                    const int cc0 = (c0 >> 3) & 7;  // first 16-byte chunk of this step inside the 64-column block
                     if (relu) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < CW / 8; ++g) {
                             uint4 pk = make_uint4(pack2_relu(f[8 * g], f[8 * g + 1]), pack2_relu(f[8 * g + 2], f[8 * g + 3]),
                                                   pack2_relu(f[8 * g + 4], f[8 * g + 5]), pack2_relu(f[8 * g + 6], f[8 * g + 7]));
-                            *reinterpret_cast<uint4 *>(dst + ((((cc0 + g)) ^ (row & 7)) << 4)) = pk;
+                            *reinterpret_cast<uint4 *>(dst + (((cc0 + g) ^ (row & 7)) << 4)) = pk;
                         }
                     } else {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < CW / 8; ++g) {
                             uint4 pk = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
                                                   pack2(f[8 * g + 6], f[8 * g + 7]));
-                            *reinterpret_cast<uint4 *>(dst + ((((cc0 + g)) ^ (row & 7)) << 4)) = pk;
+                            *reinterpret_cast<uint4 *>(dst + (((cc0 + g) ^ (row & 7)) << 4)) = pk;
                         }
                     }
                     return;
                 }
                 if (relu) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                    for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
                 }
                 if (p.pool == 1) {
-                    // thread = row: its 32 columns are 128 contiguous bytes of the output row.  Four 256-bit stores (one full
-                    // 32-byte sector per lane each) instead of a shared-memory transpose: the epilogue is issue-bound
-                    if (grow < p.rows) {
+                    // thread = row: its CW columns are contiguous bytes of the output row.  256-bit stores (one full 32-byte
+                    // sector per lane each) instead of a shared-memory transpose: the epilogue is issue-bound
+                    if (CW == 32 && p.tma_out) {
+                        // coalesced output without LSU pressure: the warp stages its 32 x 32 block in swizzled shared memory
+                        // (conflict-free 16-byte stores) and one lane hands it to the TMA store engine, which writes full
+                        // lines and clips rows beyond the tensor.  Direct row-per-lane stores cost one L1 wavefront per lane.
+                        unsigned char *stg = sm + p.stage_off + warp * kStageWarpBytes;
+                        if (lane == 0) bulk_wait_read0();  // the previous box of this warp has left shared memory
+                        __syncwarp();
+                        if (p.out_f32) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                *reinterpret_cast<float4 *>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                                    make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+                        }
+                        if (p.out_bf16) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                *reinterpret_cast<uint4 *>(stg + 4096 + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+                                    make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                               pack2(f[8 * g + 6], f[8 * g + 7]));
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int r0 = (int)(tile * kTileRows) + quad * 32;
+                            if (p.out_f32) tma_store_2d(&tm_f32, s_u32(stg), c0, r0);
+                            if (p.out_bf16) tma_store_2d(&tm_bf16, s_u32(stg + 4096), c0, r0);
+                            bulk_commit();
+                        }
+                    } else if (grow < p.rows) {
                         if (p.out_f32) {
                             float *o = p.out_f32 + grow * Nl + c0;
                             if (p.out_f32_vec) {
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) st_global_v8(o + 8 * g, &f[8 * g]);
+                                for (int g = 0; g < CW / 8; ++g) st_global_v8(o + 8 * g, &f[8 * g]);
                             } else {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) o[i] = f[i];
+                                for (int i = 0; i < CW; ++i) o[i] = f[i];
                             }
                         }
                         if (p.out_bf16) {
                             uint4 *o = reinterpret_cast<uint4 *>(p.out_bf16 + grow * Nl + c0);
 #pragma unroll
-                            for (int g = 0; g < 4; ++g)
+                            for (int g = 0; g < CW / 8; ++g)
                                 o[g] = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
                                                   pack2(f[8 * g + 6], f[8 * g + 7]));
                         }
                     }
                 } else {
-                    // max over the 32 rows this warp holds, for 32 columns at once: recursive halving -- at step h a lane
-                    // keeps the half of its columns selected by its lane bit and takes the partner's values for them
-                    // (31 SHFL + 31 FMNMX instead of 32 warp-wide redux); lane L ends with the max of column L
-                    float w16[16], w8[8], w4[4], w2[2];
-                    {
-                        const bool up = lane & 16;
+                    // max over the 32 rows this warp holds, for CW columns at once: recursive halving -- at the step of lane
+                    // bit h a lane keeps the half of its columns selected by that bit and takes the partner's values for them
+                    // (CW-1 SHFL + FMNMX instead of CW warp-wide redux); lane L ends with the max of column L mod CW
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float send = up ? f[i] : f[i + 16], keepv = up ? f[i + 16] : f[i];
-                            w16[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 16));
+                    for (int h = CW / 2; h >= 1; h >>= 1) {
+                        const bool up = lane & h;
+#pragma unroll
+                        for (int i = 0; i < h; ++i) {
+                            const float send = up ? f[i] : f[i + h], keepv = up ? f[i + h] : f[i];
+                            f[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, h));
                         }
                     }
-                    {
-                        const bool up = lane & 8;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float send = up ? w16[i] : w16[i + 8], keepv = up ? w16[i + 8] : w16[i];
-                            w8[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 8));
-                        }
-                    }
-                    {
-                        const bool up = lane & 4;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float send = up ? w8[i] : w8[i + 4], keepv = up ? w8[i + 4] : w8[i];
-                            w4[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 4));
-                        }
-                    }
-                    {
-                        const bool up = lane & 2;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            float send = up ? w4[i] : w4[i + 2], keepv = up ? w4[i + 2] : w4[i];
-                            w2[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 2));
-                        }
-                    }
-                    float pooled;
-                    {
-                        const bool up = lane & 1;
-                        float send = up ? w2[0] : w2[1], keepv = up ? w2[1] : w2[0];
-                        pooled = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, 1));
-                    }
-                    // lane L now holds column (L&16) + (L&8) + (L&4) + (L&2) + (L&1) == L of this 32-column chunk
+                    float pooled = f[0];
+                    if (CW == 16) pooled = fmaxf(pooled, __shfl_xor_sync(GSPN_FULL_MASK, pooled, 16));  // the two 16-row halves
                     const int keep = __float_as_int(pooled);
                     const long row0 = tile * kTileRows + quad * 32;
-                    if (row0 < p.rows) {
+                    if (row0 < p.rows && lane < CW) {
                         const long grp = row0 / p.pool;
+                        const int col = c0 + (lane & (CW - 1));
                         if (p.pool == 32) {
-                            if (p.out_f32) p.out_f32[grp * Nl + c0 + lane] = __int_as_float(keep);
-                            if (p.out_bf16) p.out_bf16[grp * Nl + c0 + lane] = __float2bfloat16_rn(__int_as_float(keep));
+                            if (p.out_f32) p.out_f32[grp * Nl + col] = __int_as_float(keep);
+                            if (p.out_bf16) p.out_bf16[grp * Nl + col] = __float2bfloat16_rn(__int_as_float(keep));
                         } else {
-                            atomicMax(reinterpret_cast<int *>(p.out_f32) + grp * Nl + c0 + lane, keep);  // out zeroed by the launcher
+                            atomicMax(reinterpret_cast<int *>(p.out_f32) + grp * Nl + col, keep);  // out zeroed by the launcher
                         }
                     }
                 }
             };
-            // software-pipelined TMEM reads: the load of the next 32 columns is in flight while this one is processed
+            // software-pipelined TMEM reads: the load of the next CW columns is in flight while this one is processed
             {
-                uint32_t va[32], vb[32];
+                uint32_t va[CW], vb[CW];
                 long long e0 = 0, e1 = 0, e2 = 0;
                 if (p.prof) e0 = clock64();
-                if (c_lo < c_hi) tc_ld32(tbase + c_lo, va);
-                for (int c0 = c_lo; c0 < c_hi; c0 += 64) {
+                if (c_lo < c_hi) tc_ld<CW>(tbase + c_lo, va);
+                for (int c0 = c_lo; c0 < c_hi; c0 += 2 * CW) {
                     tc_wait_ld();
                     if (p.prof && c0 == c_lo) e1 = clock64();
-                    if (c0 + 32 < c_hi) tc_ld32(tbase + c0 + 32, vb);
+                    if (c0 + CW < c_hi) tc_ld<CW>(tbase + c0 + CW, vb);
                     process(va, c0);
                     if (p.prof && c0 == c_lo) {
                         e2 = clock64();
                         if (blockIdx.x == 0 && tid == 0) {  // slots 8..10: first TMEM load latency, first chunk's processing, chunks
                             atomicAdd((unsigned long long *)p.prof + 8, (unsigned long long)(e1 - e0));
                             atomicAdd((unsigned long long *)p.prof + 9, (unsigned long long)(e2 - e1));
-                            atomicAdd((unsigned long long *)p.prof + 10, (unsigned long long)((c_hi - c_lo) >> 5));
+                            atomicAdd((unsigned long long *)p.prof + 10, (unsigned long long)((c_hi - c_lo) / CW));
                         }
                     }
-                    if (c0 + 32 < c_hi) {
+                    if (c0 + CW < c_hi) {
                         tc_wait_ld();
-                        if (c0 + 64 < c_hi) tc_ld32(tbase + c0 + 64, va);
-                        process(vb, c0 + 32);
+                        if (c0 + 2 * CW < c_hi) tc_ld<CW>(tbase + c0 + 2 * CW, va);
+                        process(vb, c0 + CW);
                     }
                 }
             }
@@ -561,7 +601,9 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             }
             if (p.prof) pt3 = clock64();
             tc_fence_before();
-            fence_proxy_async();  // epilogue st.shared -> visible to the tensor core's async-proxy reads
+            // epilogue st.shared -> visible to the tensor core's async-proxy reads.  The last layer wrote no operand, and its
+            // fence (MEMBAR + proxy fence) would only wait for the output stores to drain before the tile is handed back
+            if (!last) fence_proxy_async();
             __syncwarp();  // orders every lane's stores + proxy fence before the elected lane's arrive
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done) : "memory");  // tile back to the MMA issuer
             if (p.prof && blockIdx.x == 0 && tid == 0) {
@@ -574,6 +616,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, EPI == 4 ? 2 : 1) mlp_chain_ker
             }
         }
     }
+    if (p.tma_out && lane == 0) bulk_wait0();  // this warp's output boxes have been written
     }  // roles
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
@@ -682,6 +725,37 @@ extern "C" int gspn_mlp_pack_weights(int cin, int cin_padded, int cout, const fl
     return check_launch();
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda, so the library still
+// loads (and exports its symbols) on a machine without a driver
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static int tried = 0;  // benign race: the query is idempotent
+    if (!tried) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+        else
+            (void)cudaGetLastError();
+        tried = 1;
+    }
+    return fn;
+}
+// (rows x n) row-major output as a 2-D tensor map with a 32 x 32 box: 128-byte (f32) or 64-byte (bf16) swizzled box rows
+static bool encode_out_map(CUtensorMap *tm, void *base, long rows, int n, bool bf16) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || rows <= 0 || rows > 0x7fffffffL) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)n * (bf16 ? 2u : 4u)};
+    const cuuint32_t box[2] = {32u, 32u}, estr[2] = {1u, 1u};
+    return enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static long long *g_chain_prof = nullptr;  // tuning door: set by gspn_mlp_chain_set_profile, read at launch
 extern "C" void gspn_mlp_chain_set_profile(long long *prof5) { g_chain_prof = prof5; }
 
@@ -741,26 +815,45 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
         int v = atoi(e);
         if (v == 1 || v == 2) occ_cap = v;
     }
+    // pool == 1 outputs leave through TMA tensor stores from per-warp staging boxes (door: GSPN_TC_TMA_OUT=0 -> direct stores)
+    CUtensorMap tm_f32, tm_bf16;
+    memset(&tm_f32, 0, sizeof(tm_f32));
+    memset(&tm_bf16, 0, sizeof(tm_bf16));
+    p.tma_out = pool == 1;
+    if (const char *e = getenv("GSPN_TC_TMA_OUT")) p.tma_out = p.tma_out && atoi(e) != 0;
+    if (p.tma_out && out_f32) p.tma_out = encode_out_map(&tm_f32, out_f32, rows, p.N[nlayers - 1], false);
+    if (p.tma_out && out_bf16) p.tma_out = encode_out_map(&tm_bf16, out_bf16, rows, p.N[nlayers - 1], true);
     const int tries[4][2] = {{3, 4}, {2, 4}, {2, 3}, {2, 2}};
     size_t smem = 0;
     int occ = 0;
-    for (int t = 0; t < 4; ++t) {
-        const size_t rings = (size_t)p.r_bytes + (size_t)tries[t][0] * kTileBytes + (size_t)tries[t][1] * p.stage_bytes;
-        const size_t sz = 1024 + rings + affine_floats * sizeof(float);
-        if (sz > 226 * 1024) continue;
-        int o = (int)((228 * 1024) / (sz + 1024));
-        o = o > occ_tmem ? occ_tmem : o;
-        o = o > occ_cap ? occ_cap : o;
-        if (o > occ) {
-            occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1];
-            p.affine_off = (uint32_t)rings;
+    // first plan for two co-resident CTAs with 4 epilogue warps each, then for one CTA with 8 (staging is per epilogue warp)
+    for (int epi = 4; epi <= 8 && occ < 2; epi += 4) {
+        const size_t staging = p.tma_out ? (size_t)epi * kStageWarpBytes : 0;
+        const bool alias = p.tma_out && nlayers > 1 && staging <= p.r_bytes;
+        const size_t stage_extra = alias ? 0 : staging;
+        for (int t = 0; t < 4; ++t) {
+            const size_t rings = (size_t)p.r_bytes + (size_t)tries[t][0] * kTileBytes + (size_t)tries[t][1] * p.stage_bytes;
+            const size_t sz = 1024 + rings + stage_extra + affine_floats * sizeof(float);
+            if (sz > 226 * 1024) continue;
+            int o = (int)((228 * 1024) / (sz + 1024));
+            o = o > occ_tmem ? occ_tmem : o;
+            o = o > occ_cap ? occ_cap : o;
+            if (epi == 8) o = o > 1 ? 1 : o;
+            if (epi == 4 && o < 2) continue;  // 4 epilogue warps only pay off with a second CTA on the SM
+            if (o > occ) {
+                occ = o; smem = sz; p.a_stages = tries[t][0]; p.w_stages = tries[t][1];
+                p.stage_alias = alias;
+                p.stage_off = alias ? 0u : (uint32_t)rings;  // rings end on a 1 KiB boundary (swizzle atoms)
+                p.affine_off = (uint32_t)(rings + stage_extra);
+            }
         }
     }
-    // two CTAs x 4 epilogue warps per SM, or one CTA with 8 (168 registers x 352 threads fill the register file)
+    // two CTAs per SM: 4 epilogue warps each, 32 columns per TMEM read; one CTA per SM: 8 epilogue warps.  GSPN_TC_EPI=8
+    // selects 2 x (8 warps, 16 columns per read, <= 93 registers) -- measured no faster: the epilogue is bound by the
+    // SM's load/store pipe, not by per-warp latency (tuning door).
     p.epi_warps = occ >= 2 ? 4 : 8;
-    if (const char *e = getenv("GSPN_TC_EPI")) {  // tuning door
-        int v = atoi(e);
-        if (v == 4 || v == 8) p.epi_warps = v;
+    if (const char *e = getenv("GSPN_TC_EPI")) {
+        if (atoi(e) == 8) p.epi_warps = 8;
     }
     if (occ < 1) return GSPN_E_UNSUPPORTED;
     // never let more CTAs co-reside than TMEM can serve: inflate the request if shared memory alone would allow it
@@ -770,8 +863,9 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     static int smem_attr_set = 0;  // launch attribute already raised to at least this (benign race: set is idempotent)
     if ((int)smem > smem_attr_set) {
         // 227 KiB is the per-CTA limit for static + dynamic together; leave 1 KiB for the kernel's static __shared__
-        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<4, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<8, 1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         smem_attr_set = 226 * 1024;
     }
     static int sms_cached = 0;
@@ -783,10 +877,13 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     }
     long grid = (long)sms_cached * occ;
     if (grid > p.ntiles) grid = p.ntiles;
+    p.stagger_ns = 0;
+    if (const char *e = getenv("GSPN_TC_STAGGER_NS")) p.stagger_ns = (uint32_t)atoi(e);  // tuning door
     if (pool > 1 && pool != 32)
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
-    if (p.epi_warps == 4) mlp_chain_kernel<4><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p);
-    else mlp_chain_kernel<8><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p);
+    if (p.epi_warps == 4) mlp_chain_kernel<4, 2, 32><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p, tm_f32, tm_bf16);
+    else if (occ >= 2) mlp_chain_kernel<8, 2, 16><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p, tm_f32, tm_bf16);
+    else mlp_chain_kernel<8, 1, 32><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p, tm_f32, tm_bf16);
     return check_launch();
 }
 

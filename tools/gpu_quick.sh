@@ -1,11 +1,9 @@
 #!/bin/bash
-# usage: gpurun --timeout 600 -- bash tools/gpu_quick.sh <tag> "<commands...>"   (each command's output goes to gpurun_out/<tag>/)
+# usage: gpurun --timeout 600 -- bash tools/gpu_quick.sh <tag> "<commands...>"   (each command's output goes to gpurun_out/<tag>/log.txt)
 tag=$1; shift
 out=gpurun_out/$tag; mkdir -p $out
-i=0
 for cmd in "$@"; do
-  i=$((i+1))
   echo "== $cmd" >> $out/log.txt
-  ( eval "timeout 400 $cmd" ) >> $out/log.txt 2>&1
+  timeout 400 bash -c "$cmd" >> $out/log.txt 2>&1
 done
-tail -c 6000 $out/log.txt
+tail -c 7000 $out/log.txt
