@@ -7,18 +7,21 @@
 //     written by the fused ball-query+group kernel (or gspn_fp_assemble) -- each 128x64 block is one
 //     16 KiB cp.async.bulk (TMA bulk engine), no tensor map -- or, for rows of <= 8 columns, builds the
 //     tile in shared memory itself from the ball-query indices (gather mode).  Layers >0 read what the
-//     previous layer's epilogue wrote into shared memory in the same swizzled layout.
+//     previous layer's epilogue wrote into the ONE activation region, in place (the epilogue of layer l only
+//     starts when every MMA of layer l has completed, so it may overwrite that layer's operand).
 //   * B operand (weights): W^T as [cout x cin] bf16 K-major blocks, pre-swizzled once by
 //     gspn_mlp_pack_weights, streamed through a shared-memory ring by cp.async.bulk with
 //     mbarrier complete_tx; the ring runs ahead across layers and tiles.
 //   * D accumulates in TMEM (fp32, 128 lanes x cout columns); tcgen05.mma kind::f16, M=128,
 //     N<=128 per instruction; tcgen05.commit releases ring stages and signals the epilogue.
-//   * warp roles: 4 or 8 epilogue warps, an input-producer warp, a weight-producer warp and a CONVERGED
-//     MMA-issuer warp (elect.sync around tcgen05.mma only), handing tiles back and forth through the
-//     mma_done / epi_done mbarriers.
-//   * epilogue: software-pipelined tcgen05.ld 32x32b.x32 -> fp32 scale/shift (bias+BN folded) + ReLU
-//     -> bf16 -> swizzled st.shared (next layer's A); last layer: max over the nsample rows of a group by
-//     recursive-halving shuffles, or a smem-transposed coalesced fp32 store.
+//   * warp roles: 4 (two CTAs per SM) or 8 (one CTA per SM) epilogue warps, an input-producer warp, a
+//     weight-producer warp (both back off with nanosleep: their waits are not latency-critical) and a CONVERGED
+//     MMA-issuer warp (elect.sync around a block's four tcgen05.mma + commit), handing tiles back and forth through
+//     the mma_done / epi_done mbarriers.
+//   * epilogue: software-pipelined tcgen05.ld 32x32b.x32 -> fp32 scale/shift (bias+BN folded) -> ReLU fused into
+//     the bf16 conversion (cvt.rn.relu.bf16x2) -> swizzled st.shared (next layer's A); last layer: max over the
+//     nsample rows of a group by recursive-halving shuffles, or (pool == 1) per-warp swizzled staging boxes handed
+//     to TMA tensor stores (cp.async.bulk.tensor.2d, full-line writes, rows beyond the tensor clipped by the map).
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link dependency)
@@ -50,7 +53,6 @@ struct ChainParams {
     int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
     uint32_t r_bytes, stage_bytes;  // r_bytes: the activation region (hidden layers are written in place, see below)
     uint32_t affine_off;            // byte offset of the folded scale/shift table
-    uint32_t stagger_ns;            // odd CTAs start this much later (pool == 1 chains with several tiles per CTA)
     int tma_out;                    // pool == 1: output rows leave through per-warp swizzled staging + TMA tensor stores
     uint32_t stage_off;             // byte offset of the staging area (kStageWarpBytes per epilogue warp)
     int stage_alias;                // staging aliases the activation region (dead while the last layer's epilogue runs)
@@ -198,6 +200,164 @@ struct Cursor {  // position in the per-tile weight block sequence: layer, k-blo
     }
 };
 
+// ---------------------------------------------------------------- epilogue (shared by both chain kernels)
+struct EpiCtx {
+    const float *sc, *sh;  // this layer's folded scale / shift (shared memory)
+    unsigned char *outb;   // activation region the next layer reads (mid layers)
+    unsigned char *stg;    // this warp's output staging boxes (TMA output path)
+    int Nl, row, lane;     // layer width; row of the tile this thread owns (= TMEM lane); lane
+    long grow, row0;       // global row of this thread; global row of the warp's first row
+    bool last, relu;
+};
+
+// one step: CW accumulator columns of one row per thread -> affine (+ReLU) -> next layer's operand / output / max-pool
+template <int CW>
+__device__ __forceinline__ void epi_chunk(const ChainParams &p, const CUtensorMap *tm_f32, const CUtensorMap *tm_bf16, const EpiCtx &e,
+                                          const uint32_t (&v)[CW], const int c0) {
+    const int lane = e.lane, row = e.row, Nl = e.Nl;
+    float f[CW];
+    {
+        const float4 *sc4 = reinterpret_cast<const float4 *>(e.sc + c0), *sh4 = reinterpret_cast<const float4 *>(e.sh + c0);
+#pragma unroll
+        for (int g = 0; g < CW / 4; ++g) {
+            const float4 a4 = sc4[g], b4 = sh4[g];  // same address in every lane: one broadcast LDS.128 each
+            f[4 * g] = fmaf(__uint_as_float(v[4 * g]), a4.x, b4.x); f[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), a4.y, b4.y);
+            f[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), a4.z, b4.z); f[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), a4.w, b4.w);
+        }
+    }
+    if (!e.last) {
+        // ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32): no separate max per element
+        unsigned char *dst = e.outb + (size_t)(c0 >> 6) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128;
+        const int cc0 = (c0 >> 3) & 7;  // first 16-byte chunk of this step inside the 64-column block
+        if (e.relu) {
+#pragma unroll
+            for (int g = 0; g < CW / 8; ++g) {
+                uint4 pk = make_uint4(pack2_relu(f[8 * g], f[8 * g + 1]), pack2_relu(f[8 * g + 2], f[8 * g + 3]),
+                                      pack2_relu(f[8 * g + 4], f[8 * g + 5]), pack2_relu(f[8 * g + 6], f[8 * g + 7]));
+                *reinterpret_cast<uint4 *>(dst + (((cc0 + g) ^ (row & 7)) << 4)) = pk;
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < CW / 8; ++g) {
+                uint4 pk = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                      pack2(f[8 * g + 6], f[8 * g + 7]));
+                *reinterpret_cast<uint4 *>(dst + (((cc0 + g) ^ (row & 7)) << 4)) = pk;
+            }
+        }
+        return;
+    }
+    if (e.relu) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    if (p.pool == 1) {
+        if (CW == 32 && p.tma_out) {
+            // coalesced output without LSU pressure: the warp stages its 32 x 32 block in swizzled shared memory
+            // (conflict-free 16-byte stores) and one lane hands it to the TMA store engine, which writes full
+            // lines and clips rows beyond the tensor.  Direct row-per-lane stores cost one L1 wavefront per lane.
+            unsigned char *stg = e.stg;
+            if (lane == 0) bulk_wait_read0();  // the previous box of this warp has left shared memory
+            __syncwarp();
+            if (p.out_f32) {
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g)
+                    *reinterpret_cast<float4 *>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                        make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+            }
+            if (p.out_bf16) {
+#pragma unroll
+                for (int g = 0; g < CW / 8; ++g)
+                    *reinterpret_cast<uint4 *>(stg + 4096 + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+                        make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                   pack2(f[8 * g + 6], f[8 * g + 7]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                if (p.out_f32) tma_store_2d(tm_f32, s_u32(stg), c0, (int)e.row0);
+                if (p.out_bf16) tma_store_2d(tm_bf16, s_u32(stg + 4096), c0, (int)e.row0);
+                bulk_commit();
+            }
+        } else if (e.grow < p.rows) {
+            // thread = row: its CW columns are contiguous bytes of the output row; 256-bit stores (one 32-byte sector per lane)
+            if (p.out_f32) {
+                float *o = p.out_f32 + e.grow * Nl + c0;
+                if (p.out_f32_vec) {
+#pragma unroll
+                    for (int g = 0; g < CW / 8; ++g) st_global_v8(o + 8 * g, &f[8 * g]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) o[i] = f[i];
+                }
+            }
+            if (p.out_bf16) {
+                uint4 *o = reinterpret_cast<uint4 *>(p.out_bf16 + e.grow * Nl + c0);
+#pragma unroll
+                for (int g = 0; g < CW / 8; ++g)
+                    o[g] = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
+                                      pack2(f[8 * g + 6], f[8 * g + 7]));
+            }
+        }
+    } else {
+        // max over the 32 rows this warp holds, for CW columns at once: recursive halving -- at the step of lane
+        // bit h a lane keeps the half of its columns selected by that bit and takes the partner's values for them
+        // (CW-1 SHFL + FMNMX instead of CW warp-wide redux); lane L ends with the max of column L mod CW
+#pragma unroll
+        for (int h = CW / 2; h >= 1; h >>= 1) {
+            const bool up = lane & h;
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+                const float send = up ? f[i] : f[i + h], keepv = up ? f[i + h] : f[i];
+                f[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, h));
+            }
+        }
+        float pooled = f[0];
+        if (CW == 16) pooled = fmaxf(pooled, __shfl_xor_sync(GSPN_FULL_MASK, pooled, 16));  // the two 16-row halves
+        const int keep = __float_as_int(pooled);
+        if (e.row0 < p.rows && lane < CW) {
+            const long grp = e.row0 / p.pool;
+            const int col = c0 + (lane & (CW - 1));
+            if (p.pool == 32) {
+                if (p.out_f32) p.out_f32[grp * Nl + col] = __int_as_float(keep);
+                if (p.out_bf16) p.out_bf16[grp * Nl + col] = __float2bfloat16_rn(__int_as_float(keep));
+            } else {
+                atomicMax(reinterpret_cast<int *>(p.out_f32) + grp * Nl + col, keep);  // out zeroed by the launcher
+            }
+        }
+    }
+}
+
+// columns [c_lo, c_hi) of this warp's 32 rows: software-pipelined TMEM reads (the load of the next CW columns is in flight
+// while this one is processed)
+template <int CW>
+__device__ __forceinline__ void epi_columns(const ChainParams &p, const CUtensorMap *tm_f32, const CUtensorMap *tm_bf16, const EpiCtx &e,
+                                            const uint32_t tbase, const int c_lo, const int c_hi) {
+    uint32_t va[CW], vb[CW];
+    if (c_lo < c_hi) tc_ld<CW>(tbase + c_lo, va);
+    for (int c0 = c_lo; c0 < c_hi; c0 += 2 * CW) {
+        tc_wait_ld();
+        if (c0 + CW < c_hi) tc_ld<CW>(tbase + c0 + CW, vb);
+        epi_chunk<CW>(p, tm_f32, tm_bf16, e, va, c0);
+        if (c0 + CW < c_hi) {
+            tc_wait_ld();
+            if (c0 + 2 * CW < c_hi) tc_ld<CW>(tbase + c0 + 2 * CW, va);
+            epi_chunk<CW>(p, tm_f32, tm_bf16, e, vb, c0 + CW);
+        }
+    }
+    // a hidden layer whose width is 32 mod 64 leaves the upper half of its last 64-column block to the K padding of
+    // the next layer: keep it zero (the region is reused in place, an earlier, wider layer may have written there)
+    if (!e.last && (e.Nl & 63) && c_lo == 0) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        const int row = e.row;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int cc = (e.Nl >> 3) + g;
+            *reinterpret_cast<uint4 *>(e.outb + (size_t)(cc >> 3) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128 +
+                                       (((cc & 7) ^ (row & 7)) << 4)) = z;
+        }
+    }
+}
+
 // EPI epilogue warps (4: one per TMEM lane quadrant, 8: two per quadrant, each taking half the columns); MINB CTAs per SM
 // (register budget); CW columns per TMEM read (32, or 16 when 2 x 8 epilogue warps have to fit the register file)
 template <int EPI, int MINB, int CW>
@@ -258,9 +418,6 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    // de-phase the CTAs: all of them start together and run the same layer sequence, so without this every CTA reaches the
-    // output-writing last layer at the same time and the chip alternates between an HBM-write burst and HBM-idle compute
-    if (p.stagger_ns && (blockIdx.x & 1)) __nanosleep(p.stagger_ns);
     int blocks_per_tile = 0;
     for (int l = 0; l < p.nlayers; ++l) blocks_per_tile += ((p.N[l] + p.nch - 1) / p.nch) * (p.K[l] >> 6);
     const int kb0 = p.K[0] >> 6;
@@ -446,159 +603,11 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
             const int c_lo = ((Nl / CW) * half / nhalf) * CW, c_hi = ((Nl / CW) * (half + 1) / nhalf) * CW;  // this warp's columns
             unsigned char *outb = sm;
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16);
-            const bool relu = p.relu[l] != 0;
-            auto process = [&](const uint32_t (&v)[CW], const int c0) {
-                float f[CW];
-                {
-                    const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c0), *sh4 = reinterpret_cast<const float4 *>(sh + c0);
-#pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const float4 a4 = sc4[g], b4 = sh4[g];  // same address in every lane: one broadcast LDS.128 each
-                        f[4 * g] = fmaf(__uint_as_float(v[4 * g]), a4.x, b4.x); f[4 * g + 1] = fmaf(__uint_as_float(v[4 * g + 1]), a4.y, b4.y);
-                        f[4 * g + 2] = fmaf(__uint_as_float(v[4 * g + 2]), a4.z, b4.z); f[4 * g + 3] = fmaf(__uint_as_float(v[4 * g + 3]), a4.w, b4.w);
-                    }
-                }
-                if (!last) {
-                    // ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32): no separate max per element
-                    unsigned char *dst = outb + (size_t)(c0 >> 6) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128;
-                    const int cc0 = (c0 >> 3) & 7;  // first 16-byte chunk of this step inside the 64-column block
-                    if (relu) {
-#pragma unroll
-                        for (int g = 0; g < CW / 8; ++g) {
-                            uint4 pk = make_uint4(pack2_relu(f[8 * g], f[8 * g + 1]), pack2_relu(f[8 * g + 2], f[8 * g + 3]),
-                                                  pack2_relu(f[8 * g + 4], f[8 * g + 5]), pack2_relu(f[8 * g + 6], f[8 * g + 7]));
-                            *reinterpret_cast<uint4 *>(dst + (((cc0 + g) ^ (row & 7)) << 4)) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < CW / 8; ++g) {
-                            uint4 pk = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
-                                                  pack2(f[8 * g + 6], f[8 * g + 7]));
-                            *reinterpret_cast<uint4 *>(dst + (((cc0 + g) ^ (row & 7)) << 4)) = pk;
-                        }
-                    }
-                    return;
-                }
-                if (relu) {
-#pragma unroll
-                    for (int i = 0; i < CW; ++i) f[i] = fmaxf(f[i], 0.f);
-                }
-                if (p.pool == 1) {
-                    // thread = row: its CW columns are contiguous bytes of the output row.  256-bit stores (one full 32-byte
-                    // sector per lane each) instead of a shared-memory transpose: the epilogue is issue-bound
-                    if (CW == 32 && p.tma_out) {
-                        // coalesced output without LSU pressure: the warp stages its 32 x 32 block in swizzled shared memory
-                        // (conflict-free 16-byte stores) and one lane hands it to the TMA store engine, which writes full
-                        // lines and clips rows beyond the tensor.  Direct row-per-lane stores cost one L1 wavefront per lane.
-                        unsigned char *stg = sm + p.stage_off + warp * kStageWarpBytes;
-                        if (lane == 0) bulk_wait_read0();  // the previous box of this warp has left shared memory
-                        __syncwarp();
-                        if (p.out_f32) {
-#pragma unroll
-                            for (int g = 0; g < 8; ++g)
-                                *reinterpret_cast<float4 *>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                                    make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-                        }
-                        if (p.out_bf16) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-                                *reinterpret_cast<uint4 *>(stg + 4096 + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-                                    make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
-                                               pack2(f[8 * g + 6], f[8 * g + 7]));
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) {
-                            const int r0 = (int)(tile * kTileRows) + quad * 32;
-                            if (p.out_f32) tma_store_2d(&tm_f32, s_u32(stg), c0, r0);
-                            if (p.out_bf16) tma_store_2d(&tm_bf16, s_u32(stg + 4096), c0, r0);
-                            bulk_commit();
-                        }
-                    } else if (grow < p.rows) {
-                        if (p.out_f32) {
-                            float *o = p.out_f32 + grow * Nl + c0;
-                            if (p.out_f32_vec) {
-#pragma unroll
-                                for (int g = 0; g < CW / 8; ++g) st_global_v8(o + 8 * g, &f[8 * g]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < CW; ++i) o[i] = f[i];
-                            }
-                        }
-                        if (p.out_bf16) {
-                            uint4 *o = reinterpret_cast<uint4 *>(p.out_bf16 + grow * Nl + c0);
-#pragma unroll
-                            for (int g = 0; g < CW / 8; ++g)
-                                o[g] = make_uint4(pack2(f[8 * g], f[8 * g + 1]), pack2(f[8 * g + 2], f[8 * g + 3]), pack2(f[8 * g + 4], f[8 * g + 5]),
-                                                  pack2(f[8 * g + 6], f[8 * g + 7]));
-                        }
-                    }
-                } else {
-                    // max over the 32 rows this warp holds, for CW columns at once: recursive halving -- at the step of lane
-                    // bit h a lane keeps the half of its columns selected by that bit and takes the partner's values for them
-                    // (CW-1 SHFL + FMNMX instead of CW warp-wide redux); lane L ends with the max of column L mod CW
-#pragma unroll
-                    for (int h = CW / 2; h >= 1; h >>= 1) {
-                        const bool up = lane & h;
-#pragma unroll
-                        for (int i = 0; i < h; ++i) {
-                            const float send = up ? f[i] : f[i + h], keepv = up ? f[i + h] : f[i];
-                            f[i] = fmaxf(keepv, __shfl_xor_sync(GSPN_FULL_MASK, send, h));
-                        }
-                    }
-                    float pooled = f[0];
-                    if (CW == 16) pooled = fmaxf(pooled, __shfl_xor_sync(GSPN_FULL_MASK, pooled, 16));  // the two 16-row halves
-                    const int keep = __float_as_int(pooled);
-                    const long row0 = tile * kTileRows + quad * 32;
-                    if (row0 < p.rows && lane < CW) {
-                        const long grp = row0 / p.pool;
-                        const int col = c0 + (lane & (CW - 1));
-                        if (p.pool == 32) {
-                            if (p.out_f32) p.out_f32[grp * Nl + col] = __int_as_float(keep);
-                            if (p.out_bf16) p.out_bf16[grp * Nl + col] = __float2bfloat16_rn(__int_as_float(keep));
-                        } else {
-                            atomicMax(reinterpret_cast<int *>(p.out_f32) + grp * Nl + col, keep);  // out zeroed by the launcher
-                        }
-                    }
-                }
-            };
-            // software-pipelined TMEM reads: the load of the next CW columns is in flight while this one is processed
-            {
-                uint32_t va[CW], vb[CW];
-                long long e0 = 0, e1 = 0, e2 = 0;
-                if (p.prof) e0 = clock64();
-                if (c_lo < c_hi) tc_ld<CW>(tbase + c_lo, va);
-                for (int c0 = c_lo; c0 < c_hi; c0 += 2 * CW) {
-                    tc_wait_ld();
-                    if (p.prof && c0 == c_lo) e1 = clock64();
-                    if (c0 + CW < c_hi) tc_ld<CW>(tbase + c0 + CW, vb);
-                    process(va, c0);
-                    if (p.prof && c0 == c_lo) {
-                        e2 = clock64();
-                        if (blockIdx.x == 0 && tid == 0) {  // slots 8..10: first TMEM load latency, first chunk's processing, chunks
-                            atomicAdd((unsigned long long *)p.prof + 8, (unsigned long long)(e1 - e0));
-                            atomicAdd((unsigned long long *)p.prof + 9, (unsigned long long)(e2 - e1));
-                            atomicAdd((unsigned long long *)p.prof + 10, (unsigned long long)((c_hi - c_lo) / CW));
-                        }
-                    }
-                    if (c0 + CW < c_hi) {
-                        tc_wait_ld();
-                        if (c0 + 2 * CW < c_hi) tc_ld<CW>(tbase + c0 + 2 * CW, va);
-                        process(vb, c0 + CW);
-                    }
-                }
-            }
-            // a hidden layer whose width is 32 mod 64 leaves the upper half of its last 64-column block to the K padding of
-            // the next layer: keep it zero (the region is reused in place, an earlier, wider layer may have written there)
-            if (!last && (Nl & 63) && half == 0) {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int cc = (Nl >> 3) + g;
-                    *reinterpret_cast<uint4 *>(outb + (size_t)(cc >> 3) * kTileBytes + (row >> 3) * 1024 + (row & 7) * 128 +
-                                               (((cc & 7) ^ (row & 7)) << 4)) = z;
-                }
-            }
+            EpiCtx ec;
+            ec.sc = sc; ec.sh = sh; ec.outb = outb; ec.stg = sm + p.stage_off + warp * kStageWarpBytes;
+            ec.Nl = Nl; ec.row = row; ec.lane = lane; ec.grow = grow; ec.row0 = tile * kTileRows + quad * 32;
+            ec.last = last; ec.relu = p.relu[l] != 0;
+            epi_columns<CW>(p, &tm_f32, &tm_bf16, ec, tbase, c_lo, c_hi);
             if (p.prof) pt3 = clock64();
             tc_fence_before();
             // epilogue st.shared -> visible to the tensor core's async-proxy reads.  The last layer wrote no operand, and its
@@ -798,6 +807,17 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     p.nch = maxn < 128 ? maxn : 128;
     p.tmem_cols = 32;
     while (p.tmem_cols < maxn) p.tmem_cols <<= 1;
+    int sms = 148;
+    {
+        static int sms_cached = 0;
+        if (sms_cached == 0) {
+            int dev = 0, v = 148;
+            GSPN_CUDA_OK(cudaGetDevice(&dev));
+            GSPN_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+            sms_cached = v;
+        }
+        sms = sms_cached;
+    }
     // the activation region holds the widest hidden layer (hidden layers are written in place)
     int rk = 0;
     for (int l = 0; l + 1 < nlayers; ++l) {
@@ -806,6 +826,18 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     }
     p.r_bytes = (uint32_t)(rk / 64) * kTileBytes;
     p.stage_bytes = (uint32_t)p.nch * 128u;
+    // pool == 1 outputs leave through TMA tensor stores from per-warp staging boxes (door: GSPN_TC_TMA_OUT=0 -> direct stores)
+    CUtensorMap tm_f32, tm_bf16;
+    memset(&tm_f32, 0, sizeof(tm_f32));
+    memset(&tm_bf16, 0, sizeof(tm_bf16));
+    p.tma_out = pool == 1;
+    if (const char *e = getenv("GSPN_TC_TMA_OUT")) p.tma_out = p.tma_out && atoi(e) != 0;
+    if (p.tma_out && out_f32) p.tma_out = encode_out_map(&tm_f32, out_f32, rows, p.N[nlayers - 1], false);
+    if (p.tma_out && out_bf16) p.tma_out = encode_out_map(&tm_bf16, out_bf16, rows, p.N[nlayers - 1], true);
+    cudaStream_t s = as_stream(stream);
+    if (pool > 1 && pool != 32)
+        GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
+
     // Shared-memory plan: [activation region | input ring | weight ring | affine table].
     // Pick the deepest rings that still give the best CTA co-residency (a second CTA on the SM overlaps its MMAs with
     // this one's epilogue); TMEM (512 columns/SM) and the register file bound co-residency too.
@@ -815,14 +847,6 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
         int v = atoi(e);
         if (v == 1 || v == 2) occ_cap = v;
     }
-    // pool == 1 outputs leave through TMA tensor stores from per-warp staging boxes (door: GSPN_TC_TMA_OUT=0 -> direct stores)
-    CUtensorMap tm_f32, tm_bf16;
-    memset(&tm_f32, 0, sizeof(tm_f32));
-    memset(&tm_bf16, 0, sizeof(tm_bf16));
-    p.tma_out = pool == 1;
-    if (const char *e = getenv("GSPN_TC_TMA_OUT")) p.tma_out = p.tma_out && atoi(e) != 0;
-    if (p.tma_out && out_f32) p.tma_out = encode_out_map(&tm_f32, out_f32, rows, p.N[nlayers - 1], false);
-    if (p.tma_out && out_bf16) p.tma_out = encode_out_map(&tm_bf16, out_bf16, rows, p.N[nlayers - 1], true);
     const int tries[4][2] = {{3, 4}, {2, 4}, {2, 3}, {2, 2}};
     size_t smem = 0;
     int occ = 0;
@@ -848,41 +872,22 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
             }
         }
     }
-    // two CTAs per SM: 4 epilogue warps each, 32 columns per TMEM read; one CTA per SM: 8 epilogue warps.  GSPN_TC_EPI=8
-    // selects 2 x (8 warps, 16 columns per read, <= 93 registers) -- measured no faster: the epilogue is bound by the
-    // SM's load/store pipe, not by per-warp latency (tuning door).
+    // two CTAs per SM: 4 epilogue warps each; one CTA per SM: 8 epilogue warps (two per TMEM lane quadrant)
     p.epi_warps = occ >= 2 ? 4 : 8;
-    if (const char *e = getenv("GSPN_TC_EPI")) {
-        if (atoi(e) == 8) p.epi_warps = 8;
-    }
     if (occ < 1) return GSPN_E_UNSUPPORTED;
     // never let more CTAs co-reside than TMEM can serve: inflate the request if shared memory alone would allow it
     const size_t min_smem = (size_t)(228 * 1024) / (occ + 1) - 1024 + 1;
     if (smem < min_smem) smem = min_smem;
-    cudaStream_t s = as_stream(stream);
     static int smem_attr_set = 0;  // launch attribute already raised to at least this (benign race: set is idempotent)
     if ((int)smem > smem_attr_set) {
         // 227 KiB is the per-CTA limit for static + dynamic together; leave 1 KiB for the kernel's static __shared__
         GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<4, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<8, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         GSPN_CUDA_OK(cudaFuncSetAttribute(mlp_chain_kernel<8, 1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         smem_attr_set = 226 * 1024;
     }
-    static int sms_cached = 0;
-    if (sms_cached == 0) {
-        int dev = 0, sms = 148;
-        GSPN_CUDA_OK(cudaGetDevice(&dev));
-        GSPN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        sms_cached = sms;
-    }
-    long grid = (long)sms_cached * occ;
+    long grid = (long)sms * occ;
     if (grid > p.ntiles) grid = p.ntiles;
-    p.stagger_ns = 0;
-    if (const char *e = getenv("GSPN_TC_STAGGER_NS")) p.stagger_ns = (uint32_t)atoi(e);  // tuning door
-    if (pool > 1 && pool != 32)
-        GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
     if (p.epi_warps == 4) mlp_chain_kernel<4, 2, 32><<<(unsigned)grid, 4 * 32 + 96, smem, s>>>(p, tm_f32, tm_bf16);
-    else if (occ >= 2) mlp_chain_kernel<8, 2, 16><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p, tm_f32, tm_bf16);
     else mlp_chain_kernel<8, 1, 32><<<(unsigned)grid, 8 * 32 + 96, smem, s>>>(p, tm_f32, tm_bf16);
     return check_launch();
 }

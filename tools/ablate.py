@@ -1,5 +1,6 @@
 """Throughput ablations of the pipelined executor: what does a stage cost the STEP (not its own kernel time)?
-Replaces one op by a cached result before the graphs are captured and re-measures ms/step. Run under gpurun."""
+Replaces one op family by a cached result before the graphs are captured and re-measures ms/step; also sweeps the
+number of graph lanes.  Run under gpurun.   usage: python tools/ablate.py [depth]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +8,8 @@ from gspn_b200 import backbone, mlp_tc, ops, scenes
 from gspn_b200.engine import BackboneEngine
 
 dev = torch.device("cuda:0")
-B, N, DEPTH, STEPS = 8, 32768, 6, 24
+B, N, STEPS = 8, 32768, 32
+DEPTH = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 batches = []
 for i in range(6):
     xyz, col = scenes.scannet_like_batch(i * B, B, N)
@@ -15,52 +17,58 @@ for i in range(6):
 store, _ = backbone.random_variables(dev)
 
 
-def measure(tag):
-    eng = BackboneEngine(store, B, N, precision="bf16", depth=DEPTH, device=dev, warm_inputs=batches[0])
-    for w in range(6):
+def measure(tag, depth=DEPTH):
+    eng = BackboneEngine(store, B, N, precision="bf16", depth=depth, device=dev, warm_inputs=batches[0])
+    for w in range(depth):
         eng.submit(*batches[w % 6])
     eng.synchronize()
     cur = torch.cuda.current_stream()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(cur)
     for s in range(STEPS):
-        eng.submit(*batches[s % 6], after=a if s < DEPTH else None)
+        eng.submit(*batches[s % 6], after=a if s < depth else None)
     eng.join(cur)
     b.record(cur)
     torch.cuda.synchronize()
-    print("%-34s %.4f ms/step" % (tag, a.elapsed_time(b) / STEPS), flush=True)
+    print("%-40s depth %2d  %.4f ms/step" % (tag, depth, a.elapsed_time(b) / STEPS), flush=True)
     del eng
 
 
-measure("baseline")
-real_fps = ops.farthest_point_sample
-cache = {}
+def cached(fn, keyfn):
+    cache = {}
+
+    def wrapper(*args, **kw):
+        key = keyfn(*args, **kw)
+        if key not in cache:
+            cache[key] = fn(*args, **kw)
+        return cache[key]
+    return wrapper
 
 
-def fake_fps(npoint, inp):
-    if inp.shape[1] != N:
-        return real_fps(npoint, inp)
-    key = (npoint, tuple(inp.shape))
-    if key not in cache:
-        cache[key] = real_fps(npoint, inp)
-    return cache[key]
+def shp(t):
+    return None if t is None else tuple(t.shape)
 
 
-ops.farthest_point_sample = fake_fps
+for d in (1, 2, 4, 8, 12, 16):
+    measure("baseline", d)
+
+real = {"fps": ops.farthest_point_sample, "chain": mlp_tc.mlp_chain, "chain_g": mlp_tc.mlp_chain_gather, "three_nn": ops.three_nn,
+        "qbp": ops.query_ball_point, "bqg": ops.ballquery_group, "fpi": mlp_tc.fp_interp_mlp}
+
+ops.farthest_point_sample = cached(real["fps"], lambda npoint, inp: (npoint, shp(inp)) if inp.shape[1] == N else (npoint, shp(inp), id(inp)))
 measure("without FPS level 1")
-ops.farthest_point_sample = lambda npoint, inp: cache.setdefault((npoint, tuple(inp.shape)), real_fps(npoint, inp))
+ops.farthest_point_sample = cached(real["fps"], lambda npoint, inp: (npoint, shp(inp)))
 measure("without any FPS")
-ops.farthest_point_sample = real_fps
-real_chain = mlp_tc.mlp_chain
-ccache = {}
-
-
-def fake_chain(a_img, rows, k0, layers, first_perm, pool, want_bf16=False):
-    key = (rows, k0, pool, want_bf16)
-    if key not in ccache:
-        ccache[key] = real_chain(a_img, rows, k0, layers, first_perm, pool, want_bf16)
-    return ccache[key]
-
-
-mlp_tc.mlp_chain = fake_chain
+mlp_tc.mlp_chain = cached(real["chain"], lambda a_img, rows, k0, layers, first_perm, pool, want_bf16=False: (rows, k0, pool, want_bf16))
+mlp_tc.mlp_chain_gather = cached(real["chain_g"], lambda xyz, new_xyz, shift, points, idx, layers, first_perm, pool: (shp(idx), pool))
+measure("without FPS and MLP chains")
+ops.farthest_point_sample = real["fps"]
 measure("without MLP chains")
+mlp_tc.mlp_chain, mlp_tc.mlp_chain_gather = real["chain"], real["chain_g"]
+ops.three_nn = cached(real["three_nn"], lambda xyz1, xyz2, **kw: (shp(xyz1), shp(xyz2), tuple(sorted(kw.items()))))
+measure("without three_nn")
+ops.three_nn = real["three_nn"]
+ops.query_ball_point = cached(real["qbp"], lambda radius, nsample, xyz1, xyz2: (radius, nsample, shp(xyz1), shp(xyz2)))
+ops.ballquery_group = cached(real["bqg"], lambda radius, nsample, xyz, new_xyz, points, dtype, *a, **k: (radius, nsample, shp(xyz), shp(new_xyz), shp(points)))
+measure("without ball query / grouping")
+ops.query_ball_point, ops.ballquery_group = real["qbp"], real["bqg"]
