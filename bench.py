@@ -211,7 +211,12 @@ def stage_costs(B, precision):
         ld = ((c + 3 + 63) // 64) * 64 if precision == "bf16" else c + 3
         costs[s + ":fps"] = ("hbm", B * (12 * n + 4 * m))
         costs[s + ":gather"] = ("hbm", B * m * (4 + 12 + 12))
-        costs[s + ":ballquery_group"] = ("hbm", B * (12 * n + 12 * m + n * c * 4 + 4 * m * k + 4 * m + m * k * ld * e_out))
+        if precision == "bf16" and c + 3 <= 8:
+            # narrow rows (SA1): the chain kernel gathers its first operand itself from the indices (mlp_tc.gather_ok), so
+            # the search stage reads the cloud + queries and writes only idx / pts_cnt -- no grouped tensor in HBM
+            costs[s + ":ballquery_group"] = ("hbm", B * (12 * n + 12 * m + 4 * m * k + 4 * m))
+        else:
+            costs[s + ":ballquery_group"] = ("hbm", B * (12 * n + 12 * m + n * c * 4 + 4 * m * k + 4 * m + m * k * ld * e_out))
         dims = [c + 3] + mlp
         costs[s + ":mlp"] = ("tensor", 2 * B * m * k * sum(a * b for a, b in zip(dims, dims[1:])))
         n, c = m, mlp[-1]

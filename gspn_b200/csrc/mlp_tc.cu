@@ -49,6 +49,8 @@ struct ChainParams {
     __nv_bfloat16 *out_bf16;
     int nch;  // weight rows (output channels) per ring stage / per MMA
     int tmem_cols;
+    int tm_bufs, slot_cols;  // accumulator buffers in TMEM (2: layer-steps alternate, so a tile's first layer is issued while
+                             // the previous tile's last epilogue still drains the other buffer) and columns per buffer
     int epi_warps;           // 4, or 8 (two warps per TMEM lane quadrant, each taking half the columns)
     int a_stages, w_stages;  // ring depths: layer-0 input blocks (16 KiB each) / weight blocks (stage_bytes each)
     uint32_t r_bytes, stage_bytes;  // r_bytes: the activation region (hidden layers are written in place, see below)
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                                                                         const __grid_constant__ CUtensorMap tm_bf16) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2];
+    __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
 
     // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the
     // MMA issuer's operands can live in uniform registers (no per-instruction R2UR waterfall)
@@ -382,11 +384,12 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
     float *affine = reinterpret_cast<float *>(sm + p.affine_off);
     const uint32_t w_full = s_u32(&bars[0]), w_empty = s_u32(&bars[kMaxStages]), a_full = s_u32(&bars[2 * kMaxStages]),
                    a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]),
-                   epi_done = s_u32(&bars[4 * kMaxStages + 1]);
+                   epi_done = s_u32(&bars[4 * kMaxStages + 2]);  // [2] each: one per TMEM accumulator buffer
 
     if (tid == 0) {
-        for (int i = 0; i < 4 * kMaxStages + 1; ++i) mb_init(s_u32(&bars[i]), 1);
+        for (int i = 0; i < 4 * kMaxStages + 2; ++i) mb_init(s_u32(&bars[i]), 1);
         mb_init(epi_done, p.epi_warps);  // one elected lane per epilogue warp arrives once per layer-step
+        mb_init(epi_done + 8, p.epi_warps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
@@ -499,10 +502,23 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
         // epilogue warps; the layer-to-layer critical path is  wait(epi_done) -> tcgen05.mma ... -> commit(mma_done)
         {
             int wu_s = 0, wu_par = 0, au_s = 0, au_par = 0;  // consumer-side stage index and round parity
-            uint32_t epi_par = 0, prof_par = 0;
-            bool first = true;
+            // Layer-steps alternate between the TMEM accumulator buffers (tm_bufs == 2).  Step s may be issued when
+            //   (1) its buffer is free: the epilogue of step s - tm_bufs has drained it, and
+            //   (2) for layers > 0, its A operand is written: the epilogue of step s - 1 is done.
+            // A tile's FIRST layer reads the input ring, so with two buffers it is issued while the previous tile's last
+            // epilogue is still running: that layer's MMA time disappears from the critical path.
+            const int NB = p.tm_bufs;
+            long seen0 = 0, seen1 = 0;  // completed epi_done phases already observed, per buffer
+            long step = 0;
+            auto wait_epi = [&](int b, long phase) {  // phases of one barrier complete, and are waited for, in order
+                if ((b ? seen1 : seen0) > phase) return;
+                mb_wait(epi_done + 8 * b, (uint32_t)(phase & 1));
+                if (b) seen1 = phase + 1; else seen0 = phase + 1;
+            };
             for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                for (int l = 0; l < p.nlayers; ++l) {
+                for (int l = 0; l < p.nlayers; ++l, ++step) {
+                    const int buf = NB == 2 ? (int)(step & 1) : 0;
+                    const long ph = NB == 2 ? (step >> 1) : step;  // this step's phase on its buffer's barriers
                     const int Nl = p.N[l], KBl = p.K[l] >> 6;
                     const int nchunks = (Nl + p.nch - 1) / p.nch;
                     // every operand wait that can be satisfied from what the rings already hold is done BEFORE the
@@ -523,8 +539,9 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                     const int last_rows = Nl - (nchunks - 1) * p.nch;
                     const uint32_t idesc_full = instr_desc(128, p.nch), idesc_last = instr_desc(128, last_rows);
                     const uint32_t a_base = (l == 0) ? 0u : Rs;
-                    if (!first) { mb_wait(epi_done, epi_par); epi_par ^= 1; }  // TMEM drained, next A operand written
-                    first = false;
+                    const uint32_t tm = tmem + buf * p.slot_cols;
+                    if (ph >= 1) wait_epi(buf, ph - 1);                               // (1) TMEM buffer drained
+                    if (l > 0 && NB == 2) wait_epi(buf ^ 1, (step - 1) >> 1);         // (2) A operand written
                     long long mt0 = 0;
                     if (p.prof) {
                         mt0 = clock64();  // slot 7: operand pre-waits + epilogue hand-off, as seen by the issuer
@@ -549,7 +566,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
-                                    tc_mma(tmem + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                                    tc_mma(tm + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
                                 tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
                             }
                             __syncwarp();
@@ -560,11 +577,11 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                             if (++au_s == p.a_stages) { au_s = 0; au_par ^= 1; }
                         }
                     }
-                    if (elect_one()) tc_commit(mma_done);
+                    if (elect_one()) tc_commit(mma_done + 8 * buf);
+                    __syncwarp();
                     if (p.prof && blockIdx.x == 0 && lane == 0) {  // profiling only: how long issuing takes, and how long the MMAs take to drain
                         long long mt1 = clock64();
-                        mb_wait(mma_done, prof_par);
-                        prof_par ^= 1;
+                        mb_wait(mma_done + 8 * buf, (uint32_t)(ph & 1));
                         long long mt2 = clock64();
                         atomicAdd((unsigned long long *)p.prof + 5, (unsigned long long)(mt1 - mt0));
                         atomicAdd((unsigned long long *)p.prof + 6, (unsigned long long)(mt2 - mt1));
@@ -574,16 +591,17 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
         }
     } else {
     // ---- epilogue warps
-    uint32_t done_par = 0;
+    long estep = 0;  // layer-steps alternate between the TMEM accumulator buffers exactly as the issuer's do
 
     for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int ao = 0;  // running offset of layer l's [scale | shift] in the affine table
-        for (int l = 0; l < p.nlayers; ++l) {
+        for (int l = 0; l < p.nlayers; ++l, ++estep) {
             const int Nl = p.N[l];
+            const int buf = p.tm_bufs == 2 ? (int)(estep & 1) : 0;
+            const long eph = p.tm_bufs == 2 ? (estep >> 1) : estep;
             long long pt0 = 0, pt1 = 0, pt2 = 0, pt3 = 0;
             if (p.prof) pt0 = pt1 = clock64();
-            mb_wait(mma_done, done_par);
-            done_par ^= 1;
+            mb_wait(mma_done + 8 * buf, (uint32_t)(eph & 1));
             tc_fence_after();
             if (p.prof) pt2 = clock64();
 
@@ -602,7 +620,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
             const long grow = tile * kTileRows + row;
             const int c_lo = ((Nl / CW) * half / nhalf) * CW, c_hi = ((Nl / CW) * (half + 1) / nhalf) * CW;  // this warp's columns
             unsigned char *outb = sm;
-            const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16);
+            const uint32_t tbase = tmem + buf * p.slot_cols + ((uint32_t)(quad * 32) << 16);
             EpiCtx ec;
             ec.sc = sc; ec.sh = sh; ec.outb = outb; ec.stg = sm + p.stage_off + warp * kStageWarpBytes;
             ec.Nl = Nl; ec.row = row; ec.lane = lane; ec.grow = grow; ec.row0 = tile * kTileRows + quad * 32;
@@ -614,7 +632,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
             // fence (MEMBAR + proxy fence) would only wait for the output stores to drain before the tile is handed back
             if (!last) fence_proxy_async();
             __syncwarp();  // orders every lane's stores + proxy fence before the elected lane's arrive
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done) : "memory");  // tile back to the MMA issuer
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(epi_done + 8 * buf) : "memory");  // buffer back to the issuer
             if (p.prof && blockIdx.x == 0 && tid == 0) {
                 long long pt4 = clock64();
                 atomicAdd((unsigned long long *)p.prof + 0, (unsigned long long)(pt1 - pt0));  // issue (loads + MMAs)
@@ -875,6 +893,11 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     // two CTAs per SM: 4 epilogue warps each; one CTA per SM: 8 epilogue warps (two per TMEM lane quadrant)
     p.epi_warps = occ >= 2 ? 4 : 8;
     if (occ < 1) return GSPN_E_UNSUPPORTED;
+    // a second accumulator buffer when the SM's 512 TMEM columns allow it for every co-resident CTA (door: GSPN_TC_BUFS=1)
+    p.slot_cols = p.tmem_cols;
+    p.tm_bufs = (2 * p.slot_cols * occ <= 512) ? 2 : 1;
+    if (const char *e = getenv("GSPN_TC_BUFS")) { if (atoi(e) == 1) p.tm_bufs = 1; }
+    p.tmem_cols = p.tm_bufs * p.slot_cols;
     // never let more CTAs co-reside than TMEM can serve: inflate the request if shared memory alone would allow it
     const size_t min_smem = (size_t)(228 * 1024) / (occ + 1) - 1024 + 1;
     if (smem < min_smem) smem = min_smem;
