@@ -212,7 +212,7 @@ int gspn_group_rows_grad(int b, int n, int c, int m, int nsample, int ld, const 
 
 /* Tuning door: when prof (device, 16 x int64, zeroed by the caller) is non-NULL, later gspn_mlp_chain launches add CTA 0's
  * cycle counts: epilogue thread 0: [1] wait for the MMAs, [2] epilogue, [3] fences+hand-off, [4] number of layer-steps;
- * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands, [7] operand + hand-off waits; [8..10] first TMEM load latency, first chunk processing, chunks.  NULL switches it off. */
+ * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands, [7] operand + hand-off waits.  NULL switches it off. */
 void gspn_mlp_chain_set_profile(long long *prof5);
 
 /* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of

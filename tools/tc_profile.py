@@ -25,5 +25,5 @@ for name, rows, cin, widths, pool in [("sa1", 8 * 2048 * 32, 6, [32, 32, 64], 32
     L.gspn_mlp_chain_set_profile(None)
     p = prof.cpu().numpy().astype(float)
     n = max(p[4], 1)
-    print("%-4s rows %7d kernel+launch %.3f ms | per layer-step cycles: issue %.0f mma_wait %.0f epilogue %.0f sync %.0f (steps %d) | MMA thread: wait %.0f issue %.0f drain %.0f | first chunk: tmem ld %.0f process %.0f, chunks/step %.2f" %
-          (name, rows, a.elapsed_time(b), p[0] / n, p[1] / n, p[2] / n, p[3] / n, int(p[4]), p[7] / n, p[5] / n, p[6] / n, p[8] / n, p[9] / n, p[10] / n), flush=True)
+    print("%-4s rows %7d kernel+launch %.3f ms | per layer-step cycles: issue %.0f mma_wait %.0f epilogue %.0f sync %.0f (steps %d) | MMA thread: wait %.0f issue %.0f drain %.0f" %
+          (name, rows, a.elapsed_time(b), p[0] / n, p[1] / n, p[2] / n, p[3] / n, int(p[4]), p[7] / n, p[5] / n, p[6] / n), flush=True)
