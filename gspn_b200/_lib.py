@@ -56,6 +56,8 @@ SIGNATURES = {
     "gspn_mlp_wgrad_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, P]),
     "gspn_group_rows_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
+    "gspn_nearest_point": (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
+    "gspn_box_shrink": (c_int, [c_int, c_int, c_int, P, P, P, P]),
 }
 
 

@@ -131,6 +131,57 @@ __global__ void __launch_bounds__(kThreads) nn_distance_grad_kernel(long total, 
     }
 }
 
+// box_shrink (models/model_rpointnet.py:529-551): tighten every box to the points it contains.  One warp per box; the
+// reference's "large number" trick is kept verbatim (outside points are shifted by -/+ gamma = 1e4 before the max / min over ALL
+// points), so an empty box yields max - min < 0 and is zeroed exactly as there.
+__global__ void __launch_bounds__(kThreads) box_shrink_kernel(int nbox_per_cloud, int n, long nbox, const float *__restrict__ box,
+                                                              const float *__restrict__ pc, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long w = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    if (w >= nbox) return;
+    const float *bx = box + w * 6;
+    const float *p = pc + (w / nbox_per_cloud) * (long)n * 3;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float half = __fdiv_rn(__ldg(bx + 3 + a), 2.0f);  // box[...,3:]/2
+        lo[a] = __fsub_rn(__ldg(bx + a), half);
+        hi[a] = __fadd_rn(__ldg(bx + a), half);
+    }
+    const float gamma = 1e4f;
+    float mx[3] = {-3.402823466e38f, -3.402823466e38f, -3.402823466e38f}, mn[3] = {3.402823466e38f, 3.402823466e38f, 3.402823466e38f};
+    for (int k = lane; k < n; k += 32) {
+        const float x = __ldg(p + 3 * k), y = __ldg(p + 3 * k + 1), z = __ldg(p + 3 * k + 2);
+        const bool in = x >= lo[0] && x <= hi[0] && y >= lo[1] && y <= hi[1] && z >= lo[2] && z <= hi[2];
+        const float shift = in ? 0.0f : gamma;  // gamma * (1 - mask)
+        mx[0] = fmaxf(mx[0], __fsub_rn(x, shift)); mx[1] = fmaxf(mx[1], __fsub_rn(y, shift)); mx[2] = fmaxf(mx[2], __fsub_rn(z, shift));
+        mn[0] = fminf(mn[0], __fadd_rn(x, shift)); mn[1] = fminf(mn[1], __fadd_rn(y, shift)); mn[2] = fminf(mn[2], __fadd_rn(z, shift));
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(GSPN_FULL_MASK, mx[a], o));
+            mn[a] = fminf(mn[a], __shfl_xor_sync(GSPN_FULL_MASK, mn[a], o));
+        }
+    if (lane == 0) {
+        bool keep = true;
+        float c[3], e[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float ext = __fsub_rn(mx[a], mn[a]);
+            keep = keep && ext > 0.0f;                                 // tf.greater(box_max - box_min, 0), all three axes
+            c[a] = __fdiv_rn(__fadd_rn(mx[a], mn[a]), 2.0f);           // (box_max + box_min) / 2
+            e[a] = __fadd_rn(ext, 1e-3f);                              // box_max - box_min + 1e-3
+        }
+        const float k = keep ? 1.0f : 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            out[w * 6 + a] = __fmul_rn(c[a], k);
+            out[w * 6 + 3 + a] = __fmul_rn(e[a], k);
+        }
+    }
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace gspn
@@ -242,3 +293,13 @@ extern "C" int gspn_nn_distance_grad(int b, int n, int m, const float *xyz1, con
     nn_distance_grad_kernel<<<blocks_for(t2), kThreads, 0, s>>>(t2, m, n, xyz2, xyz1, grad_dist2, idx2, grad_xyz2, grad_xyz1);
     return check_launch();
 }
+
+extern "C" int gspn_box_shrink(int b, int nbox, int n, const float *box, const float *pc, float *out, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && nbox >= 0 && n > 0);
+    if (b == 0 || nbox == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(box); GSPN_REQUIRE_PTR(pc); GSPN_REQUIRE_PTR(out);
+    const long total = (long)b * nbox;
+    box_shrink_kernel<<<(unsigned)ceil_div_l(total * 32, kThreads), kThreads, 0, as_stream(stream)>>>(nbox, n, total, box, pc, out);
+    return check_launch();
+}
+

@@ -24,7 +24,8 @@ namespace gspn {
 
 constexpr int kGridMinCap = 32768;
 // cell budget per cloud: about two cells per scanned point, between 32 Ki and 1 Mi
-static inline int grid_cap(int n) { long c = 2L * n; c = c < kGridMinCap ? kGridMinCap : c; c = c > (1L << 20) ? (1L << 20) : c; return (int)c; }
+// (a multiple of 4: every cloud's cell arrays then start 16-byte aligned for the vectorised scan)
+static inline int grid_cap(int n) { long c = (2L * n + 3) & ~3L; c = c < kGridMinCap ? kGridMinCap : c; c = c > (1L << 20) ? (1L << 20) : c; return (int)c; }
 constexpr int kHitCap = 512;  // per-warp hit buffer (indices) of the grid ball query
 constexpr int kGQWarps = 8;
 
@@ -67,12 +68,40 @@ __global__ void __launch_bounds__(1024) grid_bbox_kernel(int n, const float *__r
     const int cloud = blockIdx.x;
     const float *p = xyz + (size_t)cloud * n * 3;
     float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && blockDim.x == 1024) {
+        // the cloud as a flat array of 3n floats, read as coalesced float4: component c of vector v belongs to axis
+        // (4v + c) mod 3 = (v + c) mod 3; with v = tid + 1024*i and 1024 = 1 (mod 3) that is (tid + i + c) mod 3.  Accumulate by
+        // q = (i + c) mod 3 (static after unrolling i by 3) and rotate by tid mod 3 at the end.
+        const float4 *p4 = reinterpret_cast<const float4 *>(p);
+        const int nvec = (3 * n) >> 2;
+        float ql[3] = {3.4e38f, 3.4e38f, 3.4e38f}, qh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+        for (int v = threadIdx.x; v < nvec; v += 3 * 1024) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int vv = v + u * 1024;
+                if (vv < nvec) {
+                    const float4 f = __ldg(p4 + vv);
+                    ql[u % 3] = fminf(ql[u % 3], f.x); qh[u % 3] = fmaxf(qh[u % 3], f.x);
+                    ql[(u + 1) % 3] = fminf(ql[(u + 1) % 3], f.y); qh[(u + 1) % 3] = fmaxf(qh[(u + 1) % 3], f.y);
+                    ql[(u + 2) % 3] = fminf(ql[(u + 2) % 3], f.z); qh[(u + 2) % 3] = fmaxf(qh[(u + 2) % 3], f.z);
+                    ql[u % 3] = fminf(ql[u % 3], f.w); qh[u % 3] = fmaxf(qh[u % 3], f.w);  // c = 3: (u + 3) mod 3 = u
+                }
+            }
+        }
+        const int r = threadIdx.x % 3;  // axis a holds class q = (a - r) mod 3
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            float v = __ldg(p + 3 * k + a);
-            lo[a] = fminf(lo[a], v);
-            hi[a] = fmaxf(hi[a], v);
+            lo[a] = r == 0 ? ql[a] : (r == 1 ? ql[(a + 2) % 3] : ql[(a + 1) % 3]);
+            hi[a] = r == 0 ? qh[a] : (r == 1 ? qh[(a + 2) % 3] : qh[(a + 1) % 3]);
+        }
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float v = __ldg(p + 3 * k + a);
+                lo[a] = fminf(lo[a], v);
+                hi[a] = fmaxf(hi[a], v);
+            }
         }
     }
 #pragma unroll
@@ -125,44 +154,61 @@ __global__ void __launch_bounds__(256) grid_count_kernel(int n, int cap, const f
         atomicAdd(counts + (size_t)cloud * (cap + 4) + point_cell(g, __ldg(p + 3 * k), __ldg(p + 3 * k + 1), __ldg(p + 3 * k + 2)), 1);
 }
 
-// ---- 3. exclusive scan of the counts in place (cell_start) + copy to the scatter cursors, one CTA per cloud
+// ---- 3. exclusive scan of the counts in place (cell_start) + copy to the scatter cursors, one CTA per cloud.
+// 16 cells per thread per pass as four 16-byte vectors (cells beyond ncells hold zero counts and the arrays are cap+4 long),
+// block-wide scan of the per-thread sums, running carry across passes.
 __global__ void __launch_bounds__(1024) grid_scan_kernel(int cap, const GridHeader *__restrict__ hdr, int *cell_start, int *cursor) {
-    __shared__ int wsum[32];
+    __shared__ int wsum[33];
     const int cloud = blockIdx.x;
     const int ncells = hdr[cloud].ncells;
     int *cs = cell_start + (size_t)cloud * (cap + 4);
     int *cu = cursor + (size_t)cloud * (cap + 4);
-    const int per = (ncells + blockDim.x - 1) / blockDim.x;
-    const int c0 = threadIdx.x * per, c1 = min(c0 + per, ncells);
-    int sum = 0;
-    for (int c = c0; c < c1; ++c) sum += cs[c];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(GSPN_FULL_MASK, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        int v = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
-        int inc2 = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(GSPN_FULL_MASK, inc2, o);
-            if (lane >= o) inc2 += t;
+    int carry = 0;
+    for (int base = 0; base < ncells; base += 16 * 1024) {
+        const int c = base + 16 * threadIdx.x;
+        int4 v[4];
+        int sum = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            v[g] = (c + 4 * g < ncells) ? *reinterpret_cast<const int4 *>(cs + c + 4 * g) : make_int4(0, 0, 0, 0);
+            sum += v[g].x + v[g].y + v[g].z + v[g].w;
         }
-        wsum[lane] = inc2 - v;
+        int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(GSPN_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+            int inc2 = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(GSPN_FULL_MASK, inc2, o);
+                if (lane >= o) inc2 += t;
+            }
+            wsum[lane] = inc2 - w;
+            if (lane == 31) wsum[32] = inc2;
+        }
+        __syncthreads();
+        int run = carry + wsum[warp] + incl - sum;
+        carry += wsum[32];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (c + 4 * g < ncells) {
+                int4 o4;
+                o4.x = run; run += v[g].x;
+                o4.y = run; run += v[g].y;
+                o4.z = run; run += v[g].z;
+                o4.w = run; run += v[g].w;
+                *reinterpret_cast<int4 *>(cs + c + 4 * g) = o4;
+                *reinterpret_cast<int4 *>(cu + c + 4 * g) = o4;
+            }
+        }
+        __syncthreads();  // wsum is reused by the next pass
     }
-    __syncthreads();
-    int run = wsum[warp] + incl - sum;
-    for (int c = c0; c < c1; ++c) {
-        int cnt = cs[c];
-        cs[c] = run;
-        cu[c] = run;
-        run += cnt;
-    }
-    if (c1 == ncells && c0 < ncells) cs[ncells] = run;
-    if (ncells == 0 && threadIdx.x == 0) cs[0] = 0;
+    if (threadIdx.x == 0) cs[ncells] = carry;  // end marker (total number of points)
 }
 
 // ---- 4. scatter points into cell order as (x,y,z,index)

@@ -194,3 +194,23 @@ extern "C" int gspn_nn_distance(int b, int n, int m, const float *xyz1, const fl
     }
     return check_launch();
 }
+
+// One direction only: for every query the nearest reference point (lowest index on ties).  The model's brute-force
+// nearest-seed / nearest-cropped-point argmins (models/model_rpointnet.py:1136 and :1032-1033: argmin over
+// reduce_sum(square(a - b), -1)) and test.py's sklearn ball-tree 1-NN (test.py:165-166,184-185) are this search.
+extern "C" int gspn_nearest_point(int b, int n, int m, const float *queries, const float *refs, float *dist, int *idx, int rounding,
+                                  void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n >= 0 && m > 0 && b <= 65535);
+    GSPN_REQUIRE(rounding == 0 || rounding == 1);
+    if (b == 0 || n == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(queries); GSPN_REQUIRE_PTR(refs); GSPN_REQUIRE_PTR(dist); GSPN_REQUIRE_PTR(idx);
+    cudaStream_t s = as_stream(stream);
+    if (workspace != nullptr && m >= 2048 && (long)n * m >= (1L << 22)) {  // grid over the reference set
+        if (workspace_bytes < gspn_grid_workspace_bytes(b, m)) return GSPN_E_WORKSPACE;
+        return gspn_nn_one_way_grid_launch(b, n, m, queries, refs, dist, idx, rounding, workspace, s);
+    }
+    if (rounding) launch_nn<true>(b, n, m, queries, refs, dist, idx, s);
+    else launch_nn<false>(b, n, m, queries, refs, dist, idx, s);
+    return check_launch();
+}
+

@@ -247,6 +247,46 @@ def nn_distance(xyz1, xyz2, rounding="cpu"):
     return _NnDistance.apply(_cuda_f32(xyz1, "xyz1"), _cuda_f32(xyz2, "xyz2"), 1 if rounding == "gpu" else 0)
 
 
+# ----------------------------------------------------------------------------- nearest-neighbour glue around the path
+def nearest_point(queries, refs, rounding="cpu"):
+    """queries (b,n,3), refs (b,m,3) -> dist (b,n) squared, idx (b,n) i32: the nearest reference point of every query,
+    lowest index on ties.  What the model computes as tf.argmin(tf.reduce_sum(tf.square(expand(a) - expand(b)), -1), ...)
+    over a dense (b,n,m) tensor: nearest seed per point (models/model_rpointnet.py:1136), nearest cropped ROI point in
+    unmold_segmentation (:1032-1033), and test.py's sklearn ball-tree 1-NN (test.py:165-166,184-185).  Not differentiable
+    (argmin has no gradient in the reference either)."""
+    _req(queries.dim() == 3 and queries.shape[2] == 3, "nearest_point expects (b,n,3) queries shape")
+    _req(refs.dim() == 3 and refs.shape[2] == 3 and refs.shape[0] == queries.shape[0], "nearest_point expects (b,m,3) refs shape")
+    _req(refs.shape[1] > 0, "nearest_point expects at least one reference point")
+    if rounding not in ("cpu", "gpu"):
+        raise ValueError("rounding must be 'cpu' or 'gpu'")
+    q, r = _cuda_f32(queries.detach(), "queries"), _cuda_f32(refs.detach(), "refs")
+    b, n, _ = q.shape
+    m = r.shape[1]
+    dist = torch.empty((b, n), dtype=torch.float32, device=q.device)
+    idx = torch.empty((b, n), dtype=torch.int32, device=q.device)
+    ws, wsb = _grid_ws(b, m, q.device, 2048)
+    check(_lib.lib().gspn_nearest_point(b, n, m, _p(q), _p(r), _p(dist), _p(idx), 1 if rounding == "gpu" else 0, _p(ws), wsb, _stream()),
+          "nearest_point")
+    return dist, idx
+
+
+def nearest_point_index(queries, refs):
+    """argmin form of nearest_point: idx (b,n) i32 (models/model_rpointnet.py:1136 `midx`, :1033 `min_idx`)."""
+    return nearest_point(queries, refs)[1]
+
+
+def box_shrink(box, pc):
+    """box (b,num_sample,6) = (centre, extent), pc (b,num_point,3) -> (b,num_sample,6): every box shrunk to the points it
+    contains, zeroed when it contains none (models/model_rpointnet.py:529-551, same arithmetic)."""
+    _req(box.dim() == 3 and box.shape[2] == 6, "box_shrink expects (b,num_sample,6) box shape")
+    _req(pc.dim() == 3 and pc.shape[2] == 3 and pc.shape[0] == box.shape[0], "box_shrink expects (b,num_point,3) pc shape")
+    bx, p = _cuda_f32(box.detach(), "box"), _cuda_f32(pc.detach(), "pc")
+    b, s, _ = bx.shape
+    out = torch.empty_like(bx)
+    check(_lib.lib().gspn_box_shrink(b, s, p.shape[1], _p(bx), _p(p), _p(out), _stream()), "box_shrink")
+    return out
+
+
 # ----------------------------------------------------------------------------- fused / engine-level ops
 def ballquery_group(radius, nsample, xyz, new_xyz, points, grouped_dtype=torch.float32, shift=None):
     """Fused query_ball_point + group_point(xyz) - new_xyz + group_point(points) + concat

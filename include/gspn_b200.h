@@ -221,6 +221,20 @@ void gspn_mlp_chain_set_profile(long long *prof5);
 int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float *points1, const float *points2,
                      const int *idx, const float *weight, void *a_img, int ld, gspn_stream_t stream);
 
+/* ---- brute-force nearest-neighbour glue around the path ------------------------------
+ * One-directional 1-NN: for every query (b,n,3) the nearest reference point (b,m,3): squared distance dist (b,n)
+ * and index idx (b,n), lowest index on ties.  Replaces the model's dense (B,N,M) distance tensors + argmin:
+ * nearest seed per point  tf.argmin(reduce_sum(square(pc - pc_seed), -1), 2)   models/model_rpointnet.py:1136,
+ * nearest cropped ROI point in unmold_segmentation  :1032-1033, and test.py's sklearn ball-tree 1-NN
+ * (test.py:165-166,184-185).  rounding as gspn_nn_distance (0: every product and sum rounded, the TF / CPU
+ * arithmetic; 1: FMA chain).  workspace: gspn_grid_workspace_bytes(b, m) bytes or NULL (brute-force scan). */
+int gspn_nearest_point(int b, int n, int m, const float *queries, const float *refs, float *dist, int *idx, int rounding,
+                       void *workspace, size_t workspace_bytes, gspn_stream_t stream);
+/* box_shrink (models/model_rpointnet.py:529-551): box (b,nbox,6) = (centre, extent), pc (b,n,3) -> out (b,nbox,6):
+ * the tight box of the points inside each box (extent + 1e-3), all zeros for a box that holds no point or is
+ * degenerate along an axis.  The reference's gamma = 1e4 shift of outside points is reproduced operation by operation. */
+int gspn_box_shrink(int b, int nbox, int n, const float *box, const float *pc, float *out, gspn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

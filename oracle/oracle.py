@@ -174,6 +174,32 @@ def nn_distance_grad(xyz1, xyz2, grad_dist1, idx1, grad_dist2, idx2):
     return g1, g2
 
 
+# ----------------------------------------------------------------------------- nearest-neighbour glue
+def nearest_point(queries, refs, gpu_variant=False):
+    """argmin over the dense squared-distance tensor (models/model_rpointnet.py:1136, :1032-1033; test.py:165-166):
+    one direction of nn_distance, same loop and rounding (tf_nndistance.cpp:21-43), first index on ties as tf.argmin."""
+    d1, i1, _, _ = nn_distance(queries, refs, gpu_variant)
+    return d1, i1
+
+
+def box_shrink(box, pc):
+    """models/model_rpointnet.py:529-551 restated operation by operation in float32 numpy."""
+    box, pc = _f32(box), _f32(pc)
+    pc_aug = pc[:, None, :, :]                                   # (B,1,N,3)
+    box_aug = box[:, :, None, :]                                 # (B,S,1,6)
+    half = box_aug[..., 3:] / np.float32(2)
+    m = np.logical_and(pc_aug >= (box_aug[..., :3] - half), pc_aug <= (box_aug[..., :3] + half))
+    m = np.logical_and(np.logical_and(m[..., 0], m[..., 1]), m[..., 2])       # (B,S,N)
+    out_mask = (np.float32(1) - m[..., None].astype(np.float32))             # (B,S,N,1)
+    gamma = np.float32(1e4)
+    box_max = np.max(pc_aug - gamma * out_mask, axis=2)                      # (B,S,3)
+    box_min = np.min(pc_aug + gamma * out_mask, axis=2)
+    out = np.concatenate(((box_max + box_min) / np.float32(2), box_max - box_min + np.float32(1e-3)), axis=2)
+    keep = (box_max - box_min) > 0
+    keep = np.logical_and(np.logical_and(keep[..., 0], keep[..., 1]), keep[..., 2])[..., None].astype(np.float32)
+    return (out * keep).astype(np.float32)
+
+
 # ----------------------------------------------------------------------------- shared MLP
 def mlp_layer(x, layer, relu=True):
     """One tf_util.conv2d(1x1)+bias(+BN inference)+ReLU layer (tf_util.py:155-185,515-534).

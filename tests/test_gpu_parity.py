@@ -276,6 +276,38 @@ def test_nn_distance_both_roundings(cuda, oracle, b, n, m):
             assert np.array_equal(bits(g), bits(e))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,n,m", [(2, 18000, 256), (1, 32768, 128), (3, 777, 5), (2, 40000, 4096), (1, 5, 1)])
+def test_nearest_point_matches_oracle(cuda, oracle, b, n, m):
+    """nearest seed / nearest cropped point argmins (models/model_rpointnet.py:1136, :1032-1033), bit-exact incl. ties."""
+    rng = np.random.RandomState(n + 3 * m)
+    pc = rng.rand(b, n, 3).astype(np.float32)
+    ref = rng.rand(b, m, 3).astype(np.float32)
+    if m >= 4:
+        ref[:, m // 2] = ref[:, 1]      # duplicated reference point: the lower index must win
+        pc[:, n // 3] = ref[:, 1]
+    for rounding, variant in (("cpu", False), ("gpu", True)):
+        d, i = gspn_b200.nearest_point(T(pc, cuda), T(ref, cuda), rounding=rounding)
+        ed, ei = oracle.nearest_point(pc, ref, gpu_variant=variant)
+        assert np.array_equal(N(i), ei), rounding
+        assert np.array_equal(bits(N(d)), bits(ed)), rounding
+    assert np.array_equal(N(gspn_b200.nearest_point_index(T(pc, cuda), T(ref, cuda))), oracle.nearest_point(pc, ref)[1])
+
+
+@pytest.mark.gpu
+def test_box_shrink_matches_oracle(cuda, oracle):
+    """models/model_rpointnet.py:529-551, bit-exact (min / max / one rounded add, sub, div each)."""
+    rng = np.random.RandomState(21)
+    pc = (rng.rand(2, 18000, 3) * np.array([8, 6, 3])).astype(np.float32)
+    box = np.concatenate([rng.rand(2, 256, 3) * np.array([8, 6, 3]), 0.1 + 2.0 * rng.rand(2, 256, 3)], -1).astype(np.float32)
+    box[:, 0, :3] = 50.0          # empty box -> zeros
+    box[:, 1, 3:] = 0.0           # degenerate box
+    got = N(gspn_b200.box_shrink(T(box, cuda), T(pc, cuda)))
+    exp = oracle.box_shrink(box, pc)
+    assert np.array_equal(bits(got), bits(exp))
+    assert (got[:, 0] == 0).all()
+
+
 # ------------------------------------------------------------------------------------ backward ops (atomics: tolerance)
 GRAD_TOL = dict(rtol=1e-4, atol=1e-4)  # the reference's own gradient tests use 1e-4 (tf_grouping_op_test.py:27)
 

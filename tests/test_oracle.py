@@ -161,3 +161,38 @@ def test_oracle_matches_reference_cuda_kernels_golden(oracle, name):
         assert np.array_equal(d1.view(np.int32), g["d1"].view(np.int32)) and np.array_equal(d2.view(np.int32), g["d2"].view(np.int32))
     else:
         raise AssertionError(kind)
+
+
+def test_nearest_point_is_the_dense_argmin(oracle):
+    """models/model_rpointnet.py:1136: argmin over reduce_sum(square(pc[:, :, None] - seed[:, None]), -1); ties -> first index."""
+    rng = np.random.RandomState(11)
+    pc = rng.rand(2, 300, 3).astype(np.float32)
+    seed = rng.rand(2, 17, 3).astype(np.float32)
+    seed[:, 5] = seed[:, 3]  # an exact tie: the lower index must win, as tf.argmin returns the first minimum
+    pc[:, 7] = seed[:, 3]
+    d, i = oracle.nearest_point(pc, seed)
+    diff = pc[:, :, None, :] - seed[:, None, :, :]
+    sq = diff * diff
+    dense = (sq[..., 0] + sq[..., 1]) + sq[..., 2]  # float32, every operation rounded
+    assert np.array_equal(i, dense.argmin(-1).astype(np.int32))
+    assert np.array_equal(d, dense.min(-1))
+    assert (i[:, 7] == 3).all()
+
+
+def test_box_shrink_restatement(oracle):
+    """models/model_rpointnet.py:529-551: tight boxes, empty boxes zeroed."""
+    rng = np.random.RandomState(12)
+    pc = rng.rand(2, 500, 3).astype(np.float32)
+    box = np.concatenate([rng.rand(2, 6, 3), 0.2 + 0.4 * rng.rand(2, 6, 3)], -1).astype(np.float32)
+    box[:, 0, :3] = 5.0  # far away: holds no point
+    out = oracle.box_shrink(box, pc)
+    assert out.shape == (2, 6, 6) and (out[:, 0] == 0).all()
+    for b in range(2):
+        for s in range(1, 6):
+            lo, hi = box[b, s, :3] - box[b, s, 3:] / 2, box[b, s, :3] + box[b, s, 3:] / 2
+            inside = pc[b][np.all((pc[b] >= lo) & (pc[b] <= hi), -1)]
+            if len(inside) < 2:
+                continue
+            np.testing.assert_allclose(out[b, s, :3], (inside.max(0) + inside.min(0)) / 2, rtol=1e-6)
+            np.testing.assert_allclose(out[b, s, 3:], inside.max(0) - inside.min(0) + 1e-3, rtol=1e-5)
+
