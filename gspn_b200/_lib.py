@@ -32,6 +32,7 @@ SIGNATURES = {
     "gspn_gather_point": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_gather_point_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gspn_grid_query_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gspn_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, P, P, P, P, P, c_size_t, P]),
     "gspn_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),

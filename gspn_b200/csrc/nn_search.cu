@@ -147,9 +147,9 @@ using namespace gspn;
 
 // grid_search.cu
 int gspn_three_nn_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight, void *workspace,
-                              cudaStream_t s);
+                              size_t workspace_bytes, cudaStream_t s);
 int gspn_nn_one_way_grid_launch(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, int fma, void *workspace,
-                                cudaStream_t s);
+                                size_t workspace_bytes, cudaStream_t s);
 extern "C" size_t gspn_grid_workspace_bytes(int b, int n);
 
 extern "C" int gspn_three_nn(int b, int n, int m, const float *xyz1, const float *xyz2, float *dist, int *idx, float *weight,
@@ -160,7 +160,7 @@ extern "C" int gspn_three_nn(int b, int n, int m, const float *xyz1, const float
     cudaStream_t s = as_stream(stream);
     if (workspace != nullptr && m >= 1024 && (long)n * m >= (1L << 22)) {  // grid over the known points
         if (workspace_bytes < gspn_grid_workspace_bytes(b, m)) return GSPN_E_WORKSPACE;
-        return gspn_three_nn_grid_launch(b, n, m, xyz1, xyz2, dist, idx, weight, workspace, s);
+        return gspn_three_nn_grid_launch(b, n, m, xyz1, xyz2, dist, idx, weight, workspace, workspace_bytes, s);
     }
     if ((long)b * n >= 148L * 8 * kNNThreads * 2) {
         dim3 grid(ceil_div(n, kNNThreads * 2), b);
@@ -181,9 +181,9 @@ extern "C" int gspn_nn_distance(int b, int n, int m, const float *xyz1, const fl
     cudaStream_t s = as_stream(stream);
     if (workspace != nullptr && n >= 2048 && m >= 2048) {  // both directions through a grid over the scanned set
         if (workspace_bytes < gspn_grid_workspace_bytes(b, n > m ? n : m)) return GSPN_E_WORKSPACE;
-        int rc = gspn_nn_one_way_grid_launch(b, n, m, xyz1, xyz2, dist1, idx1, rounding, workspace, s);
+        int rc = gspn_nn_one_way_grid_launch(b, n, m, xyz1, xyz2, dist1, idx1, rounding, workspace, workspace_bytes, s);
         if (rc != GSPN_OK) return rc;
-        return gspn_nn_one_way_grid_launch(b, m, n, xyz2, xyz1, dist2, idx2, rounding, workspace, s);
+        return gspn_nn_one_way_grid_launch(b, m, n, xyz2, xyz1, dist2, idx2, rounding, workspace, workspace_bytes, s);
     }
     if (rounding) {
         launch_nn<true>(b, n, m, xyz1, xyz2, dist1, idx1, s);
@@ -207,7 +207,7 @@ extern "C" int gspn_nearest_point(int b, int n, int m, const float *queries, con
     cudaStream_t s = as_stream(stream);
     if (workspace != nullptr && m >= 2048 && (long)n * m >= (1L << 22)) {  // grid over the reference set
         if (workspace_bytes < gspn_grid_workspace_bytes(b, m)) return GSPN_E_WORKSPACE;
-        return gspn_nn_one_way_grid_launch(b, n, m, queries, refs, dist, idx, rounding, workspace, s);
+        return gspn_nn_one_way_grid_launch(b, n, m, queries, refs, dist, idx, rounding, workspace, workspace_bytes, s);
     }
     if (rounding) launch_nn<true>(b, n, m, queries, refs, dist, idx, s);
     else launch_nn<false>(b, n, m, queries, refs, dist, idx, s);

@@ -65,6 +65,14 @@ def _grid_ws(b, n_scanned, dev, min_points):
     return torch.empty((nbytes,), dtype=torch.uint8, device=dev), nbytes
 
 
+def _grid_qws(b, n_queries, n_scanned, dev, min_points):
+    """Workspace for a point-query search: the grid over the scanned set plus, for large query sets, the query ordering."""
+    if not GRID_SEARCH or n_scanned < min_points:
+        return None, 0
+    nbytes = _lib.lib().gspn_grid_query_workspace_bytes(b, n_queries, n_scanned)
+    return torch.empty((nbytes,), dtype=torch.uint8, device=dev), nbytes
+
+
 # ----------------------------------------------------------------------------- sampling
 def farthest_point_sample(npoint, inp):
     """inp (b,n,3) f32 -> (b,npoint) i32; bit-identical to farthestpointsamplingKernel."""
@@ -166,7 +174,7 @@ def three_nn(xyz1, xyz2, return_weight=False):
     dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
     idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
     w = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device) if return_weight else None
-    ws, wsb = _grid_ws(b, m, xyz1.device, 1024)
+    ws, wsb = _grid_qws(b, n, m, xyz1.device, 1024)
     check(_lib.lib().gspn_three_nn(b, n, m, _p(xyz1), _p(xyz2), _p(dist), _p(idx), _p(w), _p(ws), wsb, _stream()), "three_nn")
     return (dist, idx, w) if return_weight else (dist, idx)
 
@@ -212,7 +220,11 @@ class _NnDistance(torch.autograd.Function):
         i1 = torch.empty((b, n), dtype=torch.int32, device=dev)
         d2 = torch.empty((b, m), dtype=torch.float32, device=dev)
         i2 = torch.empty((b, m), dtype=torch.int32, device=dev)
-        ws, wsb = _grid_ws(b, max(n, m), dev, 2048) if min(n, m) >= 2048 else (None, 0)
+        ws, wsb = (None, 0)
+        if GRID_SEARCH and min(n, m) >= 2048:  # room for both directions, each with its query ordering
+            L = _lib.lib()
+            wsb = max(L.gspn_grid_query_workspace_bytes(b, n, m), L.gspn_grid_query_workspace_bytes(b, m, n))
+            ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
         check(_lib.lib().gspn_nn_distance(b, n, m, _p(xyz1), _p(xyz2), _p(d1), _p(i1), _p(d2), _p(i2), rounding, _p(ws), wsb, _stream()),
               "nn_distance")
         ctx.save_for_backward(xyz1, xyz2, i1, i2)
@@ -264,7 +276,7 @@ def nearest_point(queries, refs, rounding="cpu"):
     m = r.shape[1]
     dist = torch.empty((b, n), dtype=torch.float32, device=q.device)
     idx = torch.empty((b, n), dtype=torch.int32, device=q.device)
-    ws, wsb = _grid_ws(b, m, q.device, 2048)
+    ws, wsb = _grid_qws(b, n, m, q.device, 2048)
     check(_lib.lib().gspn_nearest_point(b, n, m, _p(q), _p(r), _p(dist), _p(idx), 1 if rounding == "gpu" else 0, _p(ws), wsb, _stream()),
           "nearest_point")
     return dist, idx

@@ -91,6 +91,10 @@ int gspn_gather_point_grad(int b, int n, int m, int c, const float *out_g, const
  * workspace (optional): gspn_grid_workspace_bytes(b, n) bytes.  With it, clouds of >= 4096 points are searched
  * through a per-cloud uniform grid instead of the O(n*m) scan -- identical results. */
 size_t gspn_grid_workspace_bytes(int b, int npoints_scanned);
+/* Workspace for the point-query searches (gspn_three_nn, gspn_nn_distance, gspn_nearest_point) that additionally lets them
+ * bucket a large QUERY set (>= 65536 points per cloud) and visit the queries in cell order (neighbouring threads then walk the same cells);
+ * results are identical, only the visiting order changes.  Passing just gspn_grid_workspace_bytes(b, scanned) is still valid. */
+size_t gspn_grid_query_workspace_bytes(int b, int n_queries, int npoints_scanned);
 int gspn_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
                           int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes, gspn_stream_t stream);
 /* group_point(points, idx)  tf_grouping.py:54-62; groupPointLauncher tf_grouping_g.cu:194

@@ -244,6 +244,28 @@ def test_three_nn_full_size_fp4(cuda, oracle):
     assert np.array_equal(N(idx), ei) and np.array_equal(bits(N(dist)), bits(ed))
 
 
+def test_point_queries_in_cell_order_are_identical(cuda, oracle):
+    """Query sets of >= 65536 points per cloud are visited in the cell order of their own grid (csrc/grid_search.cu
+    sort_queries): three_nn, nn_distance and nearest_point must not change by a bit, duplicates and far-away queries included."""
+    xyz1 = scenes.scannet_like_batch(70, 1, 70000)[0]
+    xyz2 = scenes.with_duplicates(oracle.gather_point(xyz1, oracle.farthest_point_sample(3000, xyz1[:, :20000])), 0.3)
+    xyz1[:, :1000] = xyz2[:, :1000]
+    xyz1[:, -50:] += np.float32(25.0)  # outside the known points' bounding box
+    a, b = T(xyz1, cuda), T(xyz2, cuda)
+    d, i = gspn_b200.three_nn(a, b)
+    ed, ei = oracle.three_nn(xyz1, xyz2)
+    assert np.array_equal(N(i), ei) and np.array_equal(bits(N(d)), bits(ed))
+    nd, ni = gspn_b200.nearest_point(a, b)
+    assert np.array_equal(N(ni), ei[..., 0]) and np.array_equal(bits(N(nd)), bits(ed[..., 0]))
+    got = [N(t) for t in gspn_b200.nn_distance(a, T(xyz1[:, ::-1].copy(), cuda))]  # 70000 x 70000: both directions ordered
+    ops.GRID_SEARCH = False
+    try:
+        ref = [N(t) for t in gspn_b200.nn_distance(a[:, :4096], T(xyz1[:, ::-1].copy(), cuda))]
+    finally:
+        ops.GRID_SEARCH = True
+    assert np.array_equal(got[1][:, :4096], ref[1]) and np.array_equal(bits(got[0][:, :4096]), bits(ref[0]))
+
+
 @pytest.mark.parametrize("c", [1, 37, 64, 128, 512])
 def test_three_interpolate_bit_exact(cuda, oracle, c):
     rng = np.random.RandomState(c)
