@@ -67,6 +67,7 @@ struct ChainParams {
     const float *g_shift;  // (b, m, 3) or null
     const float *g_pts;    // (b, n, c) f32 or null
     int g_n, g_m, g_k, g_c;
+    FastDiv g_div_k, g_div_m;  // row / nsample, query / m (rows < 2^31)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -430,35 +431,60 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
     // ---- producer warps: one lane each keeps a ring full for the whole kernel, independent of the MMA/epilogue
     // timeline, so the loads of the next layers / tiles are in flight while the epilogue warps are busy
     if (warp == p.epi_warps && p.a == nullptr) {
-        // gather producer: the whole warp; lane L builds rows L, L+32, L+64, L+96 of the tile (one 16-byte chunk each)
+        // gather producer: the whole warp; lane L builds rows L, L+32, L+64, L+96 of the tile (one 16-byte chunk each).
+        // Memory-level parallelism is what this warp lives on: the four rows' indices are loaded first (and the NEXT tile's
+        // are requested before this tile is built), then all dependent coordinate / feature gathers are issued together,
+        // and only then is anything consumed.  Row -> (query, cloud) uses the multiply-shift divider (rows < 2^31).
         int s = 0, par = 0;
         const int c = p.g_c;
         long t = blockIdx.x;
+        int ii[4], nxt[4];
+        auto load_idx = [&](long tile, int (&dst)[4]) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const long row = tile * kTileRows + lane + 32 * rr;
+                dst[rr] = (tile < p.ntiles && row < p.rows) ? __ldg(p.g_idx + row) : -1;
+            }
+        };
+        load_idx(t, nxt);
         for (int i = 0; i < total_a; ++i, t += gridDim.x) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) ii[rr] = nxt[rr];
+            load_idx(t + gridDim.x, nxt);
+            float gx[4][3], cx[4][3], sh[4][3], f[4][5];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const long row = t * kTileRows + lane + 32 * rr;
+                const bool ok = ii[rr] >= 0;
+                const uint32_t q = ok ? p.g_div_k.div((uint32_t)row) : 0u;  // global query index cloud*m + j
+                const uint32_t cloud = p.g_div_m.div(q);
+                const size_t pt = (size_t)cloud * p.g_n + (ok ? ii[rr] : 0);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    gx[rr][a] = ok ? __ldg(p.g_xyz + pt * 3 + a) : 0.f;
+                    cx[rr][a] = ok ? __ldg(p.g_ctr + (size_t)q * 3 + a) : 0.f;
+                    sh[rr][a] = (ok && p.g_shift) ? __ldg(p.g_shift + (size_t)q * 3 + a) : 0.f;
+                }
+#pragma unroll
+                for (int a = 0; a < 5; ++a) f[rr][a] = (ok && a < c) ? __ldg(p.g_pts + pt * c + a) : 0.f;
+            }
             if (i >= p.a_stages) mb_wait_relaxed(a_empty + 8 * s, (uint32_t)(par ^ 1));
             unsigned char *stage = sm + p.r_bytes + (size_t)s * kTileBytes;
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 const int r = lane + 32 * rr;
-                const long row = t * kTileRows + r;
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (row < p.rows) {
-                    const long q = row / p.g_k;  // global query index cloud*m + j
-                    const long cloud = q / p.g_m;
-                    const int ii = __ldg(p.g_idx + row);
-                    const float *px = p.g_xyz + (cloud * p.g_n + ii) * 3, *cx = p.g_ctr + q * 3;
-                    float d[3], f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                float d[3], v[8];
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        d[a] = __fsub_rn(__ldg(px + a), __ldg(cx + a));                       // grouped_xyz -= new_xyz (pointnet_util.py:42)
-                        if (p.g_shift) d[a] = __fsub_rn(d[a], __ldg(p.g_shift + q * 3 + a));  // -= shift_pred (model_rpointnet.py:56-57)
-                    }
+                for (int a = 0; a < 3; ++a) {
+                    d[a] = __fsub_rn(gx[rr][a], cx[rr][a]);             // grouped_xyz -= new_xyz (pointnet_util.py:42)
+                    if (p.g_shift) d[a] = __fsub_rn(d[a], sh[rr][a]);   // -= shift_pred (model_rpointnet.py:56-57)
+                }
 #pragma unroll
-                    for (int a = 0; a < 5; ++a)
-                        if (a < c) f[a] = __ldg(p.g_pts + (cloud * p.g_n + ii) * c + a);
+                for (int t2 = 0; t2 < 8; ++t2)  // columns [features(c) | dx dy dz | 0]; c is a runtime value <= 5
+                    v[t2] = (t2 < c) ? f[rr][t2 < 5 ? t2 : 4] : (t2 == c ? d[0] : (t2 == c + 1 ? d[1] : (t2 == c + 2 ? d[2] : 0.f)));
+                if (ii[rr] < 0) {
 #pragma unroll
-                    for (int t2 = 0; t2 < 8; ++t2)  // columns [features(c) | dx dy dz | 0]; c is a runtime value <= 5
-                        v[t2] = (t2 < c) ? f[t2 < 5 ? t2 : 4] : (t2 == c ? d[0] : (t2 == c + 1 ? d[1] : (t2 == c + 2 ? d[2] : 0.f)));
+                    for (int t2 = 0; t2 < 8; ++t2) v[t2] = 0.f;  // rows past the end of the problem
                 }
                 uint4 pk = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
                 *reinterpret_cast<uint4 *>(stage + (r >> 3) * 1024 + (r & 7) * 128 + ((r & 7) << 4)) = pk;  // chunk 0 ^ (r & 7)
@@ -934,6 +960,9 @@ extern "C" int gspn_mlp_chain_gather(int b, int n, int m, int nsample, int c, co
     ChainParams p = {};
     p.g_idx = idx; p.g_xyz = xyz; p.g_ctr = new_xyz; p.g_shift = shift_pred; p.g_pts = points;
     p.g_n = n; p.g_m = m; p.g_k = nsample; p.g_c = c;
+    if ((long)b * m * nsample >= (1L << 31)) return GSPN_E_UNSUPPORTED;  // the in-kernel row -> (query, cloud) divider is 32-bit
+    p.g_div_k = FastDiv((uint32_t)nsample);
+    p.g_div_m = FastDiv((uint32_t)m);
     return chain_launch(p, (long)b * m * nsample, nlayers, dims, nullptr, wimg, scale, shift, relu, pool, out_f32, out_bf16, stream);
 }
 
