@@ -3,7 +3,12 @@ usage: python tools/ncu_src_top.py src.csv [N]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]
+data = []
+for r in rows[2:]:  # a multi-kernel export repeats the two header rows: keep the first kernel only
+    if len(r) < len(hdr):
+        break
+    data.append(r)
 ci = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 tot = sum(int(r[ci['# Samples']]) for r in data)
