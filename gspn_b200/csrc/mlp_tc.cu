@@ -639,6 +639,13 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                 if (lane == 0) bulk_wait_read0();
                 asm volatile("bar.sync 1, %0;" ::"r"(EPI * 32) : "memory");
             }
+            if (p.tma_out && p.stage_alias && last && l > 0) {
+                // the other direction: this warp's staging boxes overlay operand bytes OTHER epilogue warps wrote one layer
+                // earlier.  That is already ordered (their epi_done arrive -> issuer -> tcgen05.commit -> this wait), but only
+                // through the tensor core's asynchronous arrive; a named barrier makes it a plain CTA-level ordering as well
+                // (compute-sanitizer racecheck cannot follow the former).  ~60 cycles per tile.
+                asm volatile("bar.sync 1, %0;" ::"r"(EPI * 32) : "memory");
+            }
             const float *sc = affine + ao, *sh = sc + Nl;
             ao += 2 * Nl;
             const int quad = warp & 3, half = warp >> 2, nhalf = EPI >> 2;

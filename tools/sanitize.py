@@ -27,6 +27,8 @@ dist, i3 = gspn_b200.three_nn(x[:, :500].contiguous(), x[:, :300].contiguous())
 w = torch.full((2, 500, 3), 1 / 3, device=dev)
 gspn_b200.three_interpolate(p, i3, w).sum().backward()
 gspn_b200.gather_point(p, fps % 300).sum().backward()
+gspn_b200.nearest_point(x, x[:, :200].contiguous())
+gspn_b200.box_shrink(torch.rand(2, 16, 6, device=dev), x)
 big = torch.rand(1, 140000, 3, device=dev)
 gspn_b200.farthest_point_sample(8, big)
 torch.cuda.synchronize()
