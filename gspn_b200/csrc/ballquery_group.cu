@@ -71,20 +71,24 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // grid = (ceil(m / (kBQWarps*QPW)), b).  dynamic smem: 2 point tiles + per-warp index rows.
+// qpc = queries per CTA (<= kBQWarps*QPW).  With fewer queries than warps the idle warps skip the search and the whole CTA writes
+// the neighbourhood rows together: small, wide levels (SA3: 1024 queries x 131 channels, SA4: 256 x 259) otherwise run on a
+// handful of warps that each copy their 32 x ld block alone.
 template <int QPW>
 __global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, float s_max, int nsample, const float *__restrict__ xyz1,
                                                                const float *__restrict__ xyz2, int *__restrict__ idx,
-                                                               int *__restrict__ pts_cnt, GroupArgs g) {
+                                                               int *__restrict__ pts_cnt, GroupArgs g, int qpc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tiles = reinterpret_cast<float *>(smem_raw);                        // [2][kBQTile*3]
     int *widx = reinterpret_cast<int *>(smem_raw + 2 * kBQTile * 3 * 4);       // [kBQWarps][QPW][nsample]
     __shared__ __align__(8) uint64_t full[2];
+    __shared__ float sq[kBQWarps * QPW][3];  // query centres, for the CTA-wide row writer
 
     const int cloud = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *p = xyz1 + (size_t)cloud * n * 3;
     const float *q = xyz2 + (size_t)cloud * m * 3;
-    const int jbase = (blockIdx.x * kBQWarps + warp) * QPW;
+    const int jbase = blockIdx.x * qpc + warp * QPW;
     // TMA bulk path needs the cloud base 16B aligned; tile starts are then aligned too (kBQTile*12 % 16 == 0)
     const bool bulk = ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
 
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, flo
 #pragma unroll
     for (int t = 0; t < QPW; ++t) {
         int j = jbase + t;
-        bool ok = j < m;
+        bool ok = j < m && warp * QPW + t < qpc;
         int jj = ok ? j : 0;
         qx[t] = __ldg(q + 3 * jj); qy[t] = __ldg(q + 3 * jj + 1); qz[t] = __ldg(q + 3 * jj + 2);
         cnt[t] = ok ? 0 : nsample;  // out-of-range queries are born finished
@@ -173,10 +177,11 @@ __global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, flo
     if (bulk && t + 1 < ntiles) mbar_wait(&full[(t + 1) & 1], ((t + 1) >> 1) & 1);
 
     __syncwarp();
+    const bool coop = g.grouped && qpc < kBQWarps * QPW;
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
         int j = jbase + u;
-        if (j >= m) continue;
+        if (j >= m || warp * QPW + u >= qpc) continue;
         int cn = cnt[u];
         int first = cn > 0 ? myidx[u * nsample] : 0;  // zero-hit row: zeros (reference leaves it unwritten)
         __syncwarp();
@@ -187,7 +192,19 @@ __global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, flo
         }
         if (lane == 0) pts_cnt[(size_t)cloud * m + j] = cn;
         __syncwarp();
-        if (g.grouped) write_group(g, n, m, nsample, cloud, j, myidx + u * nsample, xyz1, qx[u], qy[u], qz[u], lane);
+        if (coop) {
+            if (lane == 0) { sq[warp * QPW + u][0] = qx[u]; sq[warp * QPW + u][1] = qy[u]; sq[warp * QPW + u][2] = qz[u]; }
+        } else if (g.grouped) {
+            write_group(g, n, m, nsample, cloud, j, myidx + u * nsample, xyz1, qx[u], qy[u], qz[u], lane);
+        }
+    }
+    if (coop) {  // CTA-uniform
+        __syncthreads();
+        for (int uq = 0; uq < qpc; ++uq) {
+            const int j = blockIdx.x * qpc + uq;
+            if (j >= m) break;
+            write_group(g, n, m, nsample, cloud, j, widx + (size_t)uq * nsample, xyz1, sq[uq][0], sq[uq][1], sq[uq][2], threadIdx.x, kBQThreads);
+        }
     }
 }
 
@@ -215,11 +232,23 @@ static int launch_ballquery(int b, int n, int m, float radius, int nsample, cons
     if ((size_t)qpw * nsample * 4 * kBQWarps > 96 * 1024) qpw = 1;
     size_t smem = (size_t)2 * kBQTile * 3 * 4 + (size_t)kBQWarps * qpw * nsample * 4;
     if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;
-    dim3 grid(ceil_div(m, kBQWarps * qpw), b);
+    // queries per CTA: all warps search unless that leaves the GPU with only a few CTAs of row-copying warps; then fewer
+    // queries per CTA (1, 2 or 4) and the CTA writes their rows together (door: GSPN_BQ_QPC)
+    // measured on B200 (bench stage times): SA3 (n=512, 1024 queries, ld 192) 30.6 -> 19.3 us, SA4 (n=128, 256 queries, ld 320)
+    // 38.3 -> 12.6 us at one query per CTA; SA2 (n=2048: the scan itself is long) gets slower (39 -> 44 us) and keeps 8
+    int qpc = kBQWarps * qpw;
+    if (g.grouped && g.ld >= 64 && n <= 1024) {
+        while (qpc > 1 && (long)b * ceil_div(m, qpc) < 148L * 4) qpc >>= 1;
+    }
+    if (const char *e = getenv("GSPN_BQ_QPC")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= kBQWarps * qpw) qpc = v;
+    }
+    dim3 grid(ceil_div(m, qpc), b);
 #define GSPN_BQ_LAUNCH(Q)                                                                                                       \
     do {                                                                                                                        \
         GSPN_CUDA_OK(cudaFuncSetAttribute(ballquery_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        ballquery_kernel<Q><<<grid, kBQThreads, smem, s>>>(n, m, s_max, nsample, xyz1, xyz2, idx, pts_cnt, g);                   \
+        ballquery_kernel<Q><<<grid, kBQThreads, smem, s>>>(n, m, s_max, nsample, xyz1, xyz2, idx, pts_cnt, g, qpc);              \
     } while (0)
     if (qpw == 4) GSPN_BQ_LAUNCH(4);
     else if (qpw == 2) GSPN_BQ_LAUNCH(2);

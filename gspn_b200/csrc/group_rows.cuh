@@ -45,9 +45,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// write one neighbourhood (nsample rows) of query (cloud,j); sidx = the row's indices in smem
+// write one neighbourhood (nsample rows) of query (cloud,j); sidx = the row's indices in smem.  The (row, column) space is swept by
+// `stride` threads of which this is number `lane`: one warp (lane, 32), or a whole CTA (threadIdx.x, blockDim.x).
 __device__ __forceinline__ void write_group(const GroupArgs &g, int n, int m, int nsample, int cloud, int j, const int *sidx,
-                                            const float *__restrict__ xyz, float qx, float qy, float qz, int lane) {
+                                            const float *__restrict__ xyz, float qx, float qy, float qz, int lane, int stride = 32) {
     const long row0 = ((long)cloud * m + j) * nsample;
     RowSrc src;
     src.c = g.c;
@@ -65,7 +66,7 @@ __device__ __forceinline__ void write_group(const GroupArgs &g, int n, int m, in
         // lanes sweep the (row, column) space of the block; columns are contiguous in memory
         float *out = (float *)g.grouped;
         const int ld = g.ld;
-        for (int e = lane; e < nsample * ld; e += 32) {
+        for (int e = lane; e < nsample * ld; e += stride) {
             int s = e / ld, col = e - s * ld;
             out[(row0 + s) * ld + col] = src.at(sidx[s], col);
         }
@@ -76,7 +77,7 @@ __device__ __forceinline__ void write_group(const GroupArgs &g, int n, int m, in
     const int chunks = g.ld >> 3;
     const bool vec_f = src.pts_f && (g.c % 4 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_f) & 15u) == 0);
     const bool vec_h = src.pts_h && (g.c % 8 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_h) & 15u) == 0);
-    for (int e = lane; e < nsample * chunks; e += 32) {
+    for (int e = lane; e < nsample * chunks; e += stride) {
         int s = e / chunks, ch = e - s * chunks;
         int ii = sidx[s];
         uint4 pk;

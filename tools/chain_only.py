@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from gspn_b200 import _lib, mlp_tc
+from gspn_b200 import mlp_tc
 import test_gpu_parity as tp
 dev = torch.device("cuda:0")
 CFG = {"sa1": (8 * 2048 * 32, 6, [32, 32, 64], 32), "sa2": (8 * 512 * 32, 67, [64, 64, 128], 32), "sa3": (8 * 128 * 32, 131, [128, 128, 256], 32),
