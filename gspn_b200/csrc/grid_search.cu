@@ -256,31 +256,51 @@ __global__ void __launch_bounds__(kGQWarps * 32) ballquery_grid_kernel(int n, in
     const int cx = cell_coord(qx, g.ox, g.inv_h, g.gx), cy = cell_coord(qy, g.oy, g.inv_h, g.gy), cz = cell_coord(qz, g.oz, g.inv_h, g.gz);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.gx - 1);
     int H = 0;
-    if (x0 <= x1) {
-        for (int dz = -1; dz <= 1; ++dz) {
-            const int zc = cz + dz;
-            if (zc < 0 || zc >= g.gz) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int yc = cy + dy;
-                if (yc < 0 || yc >= g.gy) continue;
+    {
+        // The 3x3x3 block is nine contiguous ranges of the cell-sorted array (three x-adjacent cells each).  Lanes 0..8 fetch
+        // one range's bounds each -- one parallel round trip instead of nine dependent ones -- and the ranges are then walked
+        // as ONE concatenated candidate list, 32 candidates per step, instead of at least one (mostly empty) step per range.
+        int rbeg = 0, rlen = 0;
+        if (lane < 9 && x0 <= x1) {
+            const int zc = cz + lane / 3 - 1, yc = cy + lane % 3 - 1;
+            if (zc >= 0 && zc < g.gz && yc >= 0 && yc < g.gy) {
                 const int c0 = (zc * g.gy + yc) * g.gx + x0;
-                const int beg = __ldg(cs + c0), end = __ldg(cs + c0 + (x1 - x0) + 1);  // 3 x-adjacent cells are one contiguous range
-                for (int i0 = beg; i0 < end; i0 += 32) {
-                    const int i = i0 + lane;
-                    bool hit = false;
-                    int k = 0;
-                    if (i < end) {
-                        const float4 p = __ldg(sp + i);
-                        k = __float_as_int(p.w);
-                        hit = !(sqdist_fma(qx, qy, qz, p.x, p.y, p.z) > s_max);  // same operands, same rounding as the ordered scan
-                    }
-                    const unsigned bal = __ballot_sync(GSPN_FULL_MASK, hit);
-                    if (bal) {
-                        const int pos = H + __popc(bal & ((1u << lane) - 1u));
-                        if (hit && pos < kHitCap) hits[pos] = k;
-                        H += __popc(bal);
-                    }
-                }
+                rbeg = __ldg(cs + c0);
+                rlen = __ldg(cs + c0 + (x1 - x0) + 1) - rbeg;
+            }
+        }
+        int incl = rlen;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int t = __shfl_up_sync(GSPN_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int excl = incl - rlen;
+        const int T = __shfl_sync(GSPN_FULL_MASK, incl, 8);  // candidates in the block
+        int pre[9], bg[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            pre[r] = __shfl_sync(GSPN_FULL_MASK, excl, r);
+            bg[r] = __shfl_sync(GSPN_FULL_MASK, rbeg, r);
+        }
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            const int t = t0 + lane;
+            bool hit = false;
+            int k = 0;
+            if (t < T) {
+                int base = bg[0], p0 = pre[0];  // the last range whose start offset is <= t (empty ranges share their successor's)
+#pragma unroll
+                for (int r = 1; r < 9; ++r)
+                    if (t >= pre[r]) { base = bg[r]; p0 = pre[r]; }
+                const float4 p = __ldg(sp + base + (t - p0));
+                k = __float_as_int(p.w);
+                hit = !(sqdist_fma(qx, qy, qz, p.x, p.y, p.z) > s_max);  // same operands, same rounding as the ordered scan
+            }
+            const unsigned bal = __ballot_sync(GSPN_FULL_MASK, hit);
+            if (bal) {
+                const int pos = H + __popc(bal & ((1u << lane) - 1u));
+                if (hit && pos < kHitCap) hits[pos] = k;
+                H += __popc(bal);
             }
         }
     }
@@ -373,7 +393,32 @@ __global__ void __launch_bounds__(128) three_nn_grid_kernel(int n, int m, int ca
         b1 = b2 = b3 = __int_as_float(0x7f800000);  // +inf: 1e40 as float (tf_interpolate.cpp:66,91)
         i1 = i2 = i3 = 0;
         const int xa = max(cx - R, 0), xb = min(cx + R, g.gx - 1);
-        if (xa <= xb) {
+        if (R == 1) {
+            // first pass (almost always the only one): the bounds of all nine ranges are requested together, so the thread
+            // pays one memory round trip for them instead of nine dependent ones
+            int bb[9], ee[9];
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                const int zc = cz + r / 3 - 1, yc = cy + r % 3 - 1;
+                const bool ok = xa <= xb && zc >= 0 && zc < g.gz && yc >= 0 && yc < g.gy;
+                const int c0 = ok ? (zc * g.gy + yc) * g.gx + xa : 0;
+                bb[r] = ok ? __ldg(cs + c0) : 0;
+                ee[r] = ok ? __ldg(cs + c0 + (xb - xa) + 1) : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                for (int i = bb[r]; i < ee[r]; ++i) {
+                    const float4 p = __ldg(sp + i);
+                    const float d = FMA ? sqdist_fma(p.x, p.y, p.z, x1, y1, z1) : sqdist_nofma(p.x, p.y, p.z, x1, y1, z1);
+                    const int k = __float_as_int(p.w);
+                    if (TOP1) {
+                        if (d < b1 || (d == b1 && k < i1)) { b1 = d; i1 = k; }
+                    } else {
+                        insert3(d, k, b1, b2, b3, i1, i2, i3);
+                    }
+                }
+            }
+        } else if (xa <= xb) {
             for (int zc = max(cz - R, 0); zc <= min(cz + R, g.gz - 1); ++zc)
                 for (int yc = max(cy - R, 0); yc <= min(cy + R, g.gy - 1); ++yc) {
                     const int c0 = (zc * g.gy + yc) * g.gx + xa;
