@@ -523,6 +523,11 @@ TC_CASES = [
     ("fp1_wide", 300, 768, [256, 256], 1),
     ("ctx_pool256", 1024, 6, [64, 128, 256], 256),
     ("four_layers", 640, 40, [64, 32, 96, 160], 64),
+    # persistent regime: several tiles per CTA (ring wrap-around, alternating TMEM buffers with early first-layer issue,
+    # output staging aliased on the activation region, rows not a multiple of the tile)
+    ("fp4_many_tiles", 150000, 131, [128, 128, 128], 1),
+    ("sa2_many_tiles", 131072, 67, [64, 64, 128], 32),
+    ("fp3_many_tiles_n256", 70001, 320, [256, 128], 1),
 ]
 
 
