@@ -161,6 +161,11 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// The same descriptor as two 32-bit words: everything but the 14-bit start address is constant, so the issuer steps through
+// ring stages and k-slices (+32 bytes = +2) with 32-bit adds on the low word only (no carry: shared memory ends below 2^18).
+constexpr uint32_t kDescHi = 0x40004040u;  // SBO = 64 (bits 32-45), version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
 __device__ __forceinline__ uint32_t instr_desc(int m, int n) {
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
+    __shared__ int4 ltab[kMaxLayers];  // per layer, for the issuer: k-blocks, n-chunks, instruction descriptors (full / last chunk)
 
     // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the
     // MMA issuer's operands can live in uniform registers (no per-instruction R2UR waterfall)
@@ -387,6 +393,10 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                    a_empty = s_u32(&bars[3 * kMaxStages]), mma_done = s_u32(&bars[4 * kMaxStages]),
                    epi_done = s_u32(&bars[4 * kMaxStages + 2]);  // [2] each: one per TMEM accumulator buffer
 
+    if (tid < p.nlayers) {
+        const int nchunks = (p.N[tid] + p.nch - 1) / p.nch;
+        ltab[tid] = make_int4(p.K[tid] >> 6, nchunks, (int)instr_desc(128, p.nch), (int)instr_desc(128, p.N[tid] - (nchunks - 1) * p.nch));
+    }
     if (tid == 0) {
         for (int i = 0; i < 4 * kMaxStages + 2; ++i) mb_init(s_u32(&bars[i]), 1);
         mb_init(epi_done, p.epi_warps);  // one elected lane per epilogue warp arrives once per layer-step
@@ -534,19 +544,21 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
             // A tile's FIRST layer reads the input ring, so with two buffers it is issued while the previous tile's last
             // epilogue is still running: that layer's MMA time disappears from the critical path.
             const int NB = p.tm_bufs;
-            long seen0 = 0, seen1 = 0;  // completed epi_done phases already observed, per buffer
-            long step = 0;
-            auto wait_epi = [&](int b, long phase) {  // phases of one barrier complete, and are waited for, in order
+            int seen0 = 0, seen1 = 0;  // completed epi_done phases already observed, per buffer
+            int step = 0;
+            auto wait_epi = [&](int b, int phase) {  // phases of one barrier complete, and are waited for, in order
                 if ((b ? seen1 : seen0) > phase) return;
                 mb_wait(epi_done + 8 * b, (uint32_t)(phase & 1));
                 if (b) seen1 = phase + 1; else seen0 = phase + 1;
             };
+            const uint32_t a_lo0 = desc_lo(aring), w_lo0 = desc_lo(wring), r_lo0 = desc_lo(Rs);
+            const uint32_t w_step = p.stage_bytes >> 4;
             for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < p.nlayers; ++l, ++step) {
-                    const int buf = NB == 2 ? (int)(step & 1) : 0;
-                    const long ph = NB == 2 ? (step >> 1) : step;  // this step's phase on its buffer's barriers
-                    const int Nl = p.N[l], KBl = p.K[l] >> 6;
-                    const int nchunks = (Nl + p.nch - 1) / p.nch;
+                    const int buf = NB == 2 ? (step & 1) : 0;
+                    const int ph = NB == 2 ? (step >> 1) : step;  // this step's phase on its buffer's barriers
+                    const int4 L = ltab[l];
+                    const int KBl = L.x, nchunks = L.y;
                     // every operand wait that can be satisfied from what the rings already hold is done BEFORE the
                     // epilogue hand-off, so that after it the loop is  tcgen05.mma x4 + commit  per block
                     long long mw0 = 0;
@@ -562,9 +574,6 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                         mb_wait(w_full + 8 * st, (uint32_t)pr);
                         if (++st == p.w_stages) { st = 0; pr ^= 1; }
                     }
-                    const int last_rows = Nl - (nchunks - 1) * p.nch;
-                    const uint32_t idesc_full = instr_desc(128, p.nch), idesc_last = instr_desc(128, last_rows);
-                    const uint32_t a_base = (l == 0) ? 0u : Rs;
                     const uint32_t tm = tmem + buf * p.slot_cols;
                     if (ph >= 1) wait_epi(buf, ph - 1);                               // (1) TMEM buffer drained
                     if (l > 0 && NB == 2) wait_epi(buf ^ 1, (step - 1) >> 1);         // (2) A operand written
@@ -576,23 +585,22 @@ __global__ void __launch_bounds__(EPI * 32 + 96, MINB) mlp_chain_kernel(const Ch
                     tc_fence_after();
                     int blk = 0;
                     for (int kb = 0; kb < KBl; ++kb) {
-                        uint32_t a_addr;
+                        uint32_t a_lo;
                         if (l == 0) {
                             if (kb >= pre_a) { mb_wait(a_full + 8 * au_s, (uint32_t)au_par); tc_fence_after(); }
-                            a_addr = aring + au_s * kTileBytes;
+                            a_lo = a_lo0 + (uint32_t)au_s * (kTileBytes >> 4);
                         } else {
-                            a_addr = a_base + kb * kTileBytes;
+                            a_lo = r_lo0 + (uint32_t)kb * (kTileBytes >> 4);
                         }
-                        const uint64_t ad = smem_desc(a_addr);
                         for (int nc = 0; nc < nchunks; ++nc, ++blk) {
                             const int s = wu_s;
                             if (blk >= pre_w) { mb_wait(w_full + 8 * s, (uint32_t)wu_par); tc_fence_after(); }
-                            const uint32_t idesc = (nc == nchunks - 1) ? idesc_last : idesc_full;
-                            const uint64_t bd = smem_desc(wring + s * p.stage_bytes);
+                            const uint32_t idesc = (uint32_t)((nc == nchunks - 1) ? L.w : L.z);
+                            const uint32_t b_lo = w_lo0 + (uint32_t)s * w_step;
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16) per 64-wide block: +32 bytes = +2 in the descriptor
-                                    tc_mma(tm + nc * p.nch, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+                                    tc_mma(tm + nc * p.nch, desc64(a_lo + 2 * k), desc64(b_lo + 2 * k), idesc, (kb | k) != 0);
                                 tc_commit(w_empty + 8 * s);  // stage free once these MMAs have read it
                             }
                             __syncwarp();
