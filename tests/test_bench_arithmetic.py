@@ -1,0 +1,46 @@
+"""The roofline arithmetic of bench.py (algorithmic bytes / flops per launch) against SURVEY.md 8(d)'s figures -- no GPU."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_mlp_flops_match_survey_8d():
+    costs = _bench().stage_costs(8, "bf16")
+    sa = [costs["layer%d:mlp" % i][1] / 1e9 for i in range(1, 5)]
+    fp = [costs["fa_layer%d:mlp" % i][1] / 1e9 for i in range(1, 5)]
+    for got, exp in zip(sa, (3.42, 4.35, 4.32, 4.31)):   # grouped MLP + max
+        assert abs(got - exp) < 0.01, (got, exp)
+    for got, exp in zip(fp, (0.54, 1.34, 3.76, 25.97)):  # 0.5 + 1.3 + 3.8 + 26.0 = 31.6 GFLOP
+        assert abs(got - exp) < 0.01, (got, exp)
+    assert all(costs[k][0] == "tensor" for k in costs if k.endswith(":mlp"))
+
+
+def test_search_and_gather_bytes():
+    b = _bench()
+    bf, f32 = b.stage_costs(8, "bf16"), b.stage_costs(8, "fp32")
+    n, m, k = 32768, 2048, 32
+    # FPS: B*(12n + 4m); SA1 in the bf16 path gathers inside the chain, so its search stage moves the cloud, the queries and
+    # writes idx / pts_cnt only
+    assert bf["layer1:fps"] == ("hbm", 8 * (12 * n + 4 * m))
+    assert bf["layer1:ballquery_group"] == ("hbm", 8 * (12 * n + 12 * m + 4 * m * k + 4 * m))
+    # fp32 path: the grouped (m, K, 3 + C) rows are written as fp32 (SURVEY.md 8(d) formula with e_out = 4, ld = c + 3)
+    assert f32["layer1:ballquery_group"][1] == 8 * (12 * n + 12 * m + n * 3 * 4 + 4 * m * k + 4 * m + m * k * 6 * 4)
+    # SA2 (C = 64): tile image of ld = 128 bf16 columns
+    assert bf["layer2:ballquery_group"][1] == 8 * (12 * 2048 + 12 * 512 + 2048 * 64 * 4 + 4 * 512 * 32 + 4 * 512 + 512 * 32 * 128 * 2)
+    # three_nn FP4: B*(12n + 12m + 36n)
+    assert bf["fa_layer4:three_nn"] == ("hbm", 8 * (12 * n + 12 * m + 36 * n))
+
+
+def test_peaks_loader_prefers_measured_file(tmp_path, monkeypatch):
+    b = _bench()
+    peaks = b.load_peaks()
+    assert peaks["hbm_gbs"] > 1000 and peaks["bf16_tflops_sustained"] <= peaks["bf16_tflops"] * 1.01
+    assert peaks["source"] in ("measured", "fallback")
