@@ -51,6 +51,22 @@ def test_argument_checks_need_no_gpu():
     assert L.gspn_grouped_bytes(129, 67, _lib.GSPN_DT_BF16) == 2 * 2 * 16384
 
 
+def test_glue_entry_points_validate_without_a_gpu():
+    """gspn_nearest_point / gspn_box_shrink / the query workspace size: argument checks come before any CUDA call."""
+    L = _lib.lib()
+    assert L.gspn_nearest_point(1, 8, 0, None, None, None, None, 0, None, 0, None) == _lib.GSPN_E_BAD_SHAPE     # no reference points
+    assert L.gspn_nearest_point(1, 8, 4, None, None, None, None, 2, None, 0, None) == _lib.GSPN_E_BAD_SHAPE     # rounding in {0,1}
+    assert L.gspn_nearest_point(1, 8, 4, None, None, None, None, 0, None, 0, None) == _lib.GSPN_E_NULL_PTR
+    assert L.gspn_nearest_point(0, 8, 4, None, None, None, None, 0, None, 0, None) == 0                          # empty batch: nothing to do
+    assert L.gspn_box_shrink(1, 4, 0, None, None, None, None) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_box_shrink(1, 4, 16, None, None, None, None) == _lib.GSPN_E_NULL_PTR
+    assert L.gspn_box_shrink(1, 0, 16, None, None, None, None) == 0
+    scanned = L.gspn_grid_workspace_bytes(2, 5000)
+    assert L.gspn_grid_query_workspace_bytes(2, 1000, 5000) == scanned            # small query set: the scanned set's grid only
+    assert L.gspn_grid_query_workspace_bytes(2, 70000, 5000) >= scanned + L.gspn_grid_workspace_bytes(2, 70000)
+    assert L.gspn_grid_query_workspace_bytes(0, 70000, 5000) == 0
+
+
 def test_ops_refuse_cpu_tensors():
     import pytest
     import torch
