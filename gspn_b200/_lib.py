@@ -14,6 +14,10 @@ LIB_PATH = os.path.join(_HERE, "libgspn_b200.so")
 
 GSPN_DT_F32 = 0
 GSPN_DT_BF16 = 1
+GSPN_DT_BF16X2 = 2  # split (hi | lo) tile image of the bf16x3 arithmetic
+GSPN_DT_F16 = 3
+GSPN_MLP_BF16 = 0
+GSPN_MLP_BF16X3 = 1
 
 GSPN_E_BAD_SHAPE, GSPN_E_NULL_PTR, GSPN_E_BAD_DTYPE, GSPN_E_WORKSPACE, GSPN_E_CUDA, GSPN_E_UNSUPPORTED = -1, -2, -3, -4, -5, -6
 
@@ -45,18 +49,20 @@ SIGNATURES = {
     "gspn_nn_distance_grad": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "gspn_mlp_layer_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P]),
     "gspn_max_pool_rows": (c_int, [c_long, c_int, c_int, P, P, P]),
-    "gspn_mlp_weight_image_bytes": (c_size_t, [c_int, c_int]),
-    "gspn_mlp_pack_weights": (c_int, [c_int, c_int, c_int, P, P, P, P]),
-    "gspn_mlp_chain": (c_int, [c_long, c_int, P, P, P, P, P, P, c_int, P, P, P]),
-    "gspn_mlp_chain_gather": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, c_int, P, P, P]),
+    "gspn_mlp_weight_image_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gspn_mlp_pack_weights": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P]),
+    "gspn_mlp_chain": (c_int, [c_long, c_int, P, c_int, P, P, P, P, P, c_int, P, P, c_int, c_int, P]),
+    "gspn_mlp_chain_gather": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, c_int, P, P, c_int, c_int, P]),
+    "gspn_mlp_chain_fp": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P, P, c_int, c_int, P]),
     "gspn_mlp_chain_set_profile": (None, [P]),
+    "gspn_mlp_chain_tune": (None, [c_int, c_int, c_int]),
     "gspn_col_moments_f32": (c_int, [c_long, c_int, P, P, P, P]),
     "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),
     "gspn_maxpool_argmax_f32": (c_int, [c_long, c_int, c_int, P, P, P, P]),
     "gspn_bn_act_pool_bwd_f32": (c_int, [c_long, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "gspn_mlp_wgrad_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, P]),
     "gspn_group_rows_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
-    "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P]),
+    "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_int, P]),
     "gspn_nearest_point": (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
     "gspn_box_shrink": (c_int, [c_int, c_int, c_int, P, P, P, P]),
 }

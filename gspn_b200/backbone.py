@@ -54,10 +54,11 @@ def random_variables(device, colour_channels=3, seed=7, bn_seed=8, sa_specs=SA_S
     return store, as_numpy
 
 
-def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=None, timers=None, l0_bf16=False, is_training=False,
-            bn_decay=None):
+def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=None, timers=None, l0_half=None, l0_f32=True,
+            is_training=False, bn_decay=None):
     """xyz (b,n,3), colour (b,n,c) CUDA f32 -> dict(l0_points (b,n,128), l1..l4 xyz/points, indices).
-    timers: optional callable(name) -> context manager, used by bench.py to bracket stages with CUDA events."""
+    l0_half: torch.float16 / torch.bfloat16 -> also "l0_points_half", a 16-bit copy of the per-point map written by the last chain's
+    epilogue (l0_f32=False: only that copy).  timers: optional callable(name) -> context manager (bench.py stage brackets)."""
     def stage(name):
         return timers(name) if timers is not None else _null
     xs, ps, idxs = [xyz], [colour], []
@@ -71,13 +72,13 @@ def forward(xyz, colour, store, sa_specs=SA_SPECS, fp_specs=FP_SPECS, precision=
     up = ps[4]
     for i, mlp in enumerate(fp_specs):
         lvl = 3 - i
-        want_h = l0_bf16 and i == len(fp_specs) - 1 and (precision or pu.DEFAULT_PRECISION) == "bf16"
+        want_h = l0_half if (i == len(fp_specs) - 1 and not is_training) else None
         with stage("fp%d" % (i + 1)):
             up = pu.pointnet_fp_module(xs[lvl], xs[lvl + 1], ps[lvl], up, mlp, is_training, bn_decay, "fa_layer%d" % (i + 1), variables=store,
-                                       precision=precision, timers=timers, also_bf16=want_h and not is_training)
+                                       precision=precision, timers=timers, half_output=want_h, f32_output=l0_f32 or want_h is None)
     out = {"xyz": xs, "points": ps, "idx": idxs}
     if isinstance(up, tuple):
-        out["l0_points"], out["l0_points_bf16"] = up
+        out["l0_points"], out["l0_points_half"] = up
     else:
         out["l0_points"] = up
     return out

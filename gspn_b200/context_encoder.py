@@ -35,15 +35,15 @@ def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list,
     for i, (radius, nsample, mlp) in enumerate(zip(radius_list, nsample_list, mlp_list)):
         layers = store.layers(scope, "conv_prev_%d_" % i, cin, list(mlp), bn)
         rows = b * m * nsample
-        if precision == "bf16" and mlp_tc.tc_supported(layers, nsample) and mlp_tc.gather_ok(points):
+        tc = precision in pu.TC_PRECISIONS and mlp_tc.tc_supported(layers, nsample)
+        if tc and mlp_tc.gather_ok(points):
             idx, _ = ops.query_ball_point(radius, nsample, xyz, new_xyz)
             perm = (list(range(c)) + ([c, c + 1, c + 2] if (use_xyz or points is None) else [-1, -1, -1]) + [-1] * (64 - c - 3))
-            x = mlp_tc.mlp_chain_gather(xyz.contiguous(), new_xyz.contiguous(), shift_pred, None if points is None else points.contiguous(), idx,
-                                        layers, perm, nsample)
-        elif precision == "bf16" and mlp_tc.tc_supported(layers, nsample):
-            idx, _, img, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.bfloat16, shift=shift_pred)
+            x = mlp_tc.mlp_chain_gather(xyz, new_xyz, shift_pred, points, idx, layers, perm, nsample, precision)  # validates its tensors
+        elif tc:
+            idx, _, img, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, "image:" + precision, shift=shift_pred)
             perm = (list(range(c)) + ([c, c + 1, c + 2] if (use_xyz or points is None) else [-1, -1, -1]) + [-1] * (ld - c - 3))
-            x, _ = mlp_tc.mlp_chain(img, rows, ld, layers, perm, nsample)
+            x, _ = mlp_tc.mlp_chain(img, rows, ld, layers, perm, nsample, precision, k0_used=c + 3)
         else:
             idx, _, grouped, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32, shift=shift_pred)
             first = layers[0]

@@ -273,10 +273,10 @@ extern "C" int gspn_query_ball_point(int b, int n, int m, float radius, int nsam
 
 extern "C" size_t gspn_grouped_bytes(long rows, int c_plus_xyz, int grouped_dtype) {
     if (rows <= 0 || c_plus_xyz <= 0) return 0;
-    if (grouped_dtype == GSPN_DT_BF16) {
+    if (grouped_dtype == GSPN_DT_BF16 || grouped_dtype == GSPN_DT_BF16X2) {
         long tiles = ceil_div_l(rows, kTileRows);
         int ld = ceil_div(c_plus_xyz, 64) * 64;
-        return (size_t)tiles * (size_t)(ld / 64) * (size_t)kTileBytes;
+        return (size_t)tiles * (size_t)(ld / 64) * (size_t)kTileBytes * (grouped_dtype == GSPN_DT_BF16X2 ? 2 : 1);
     }
     return (size_t)rows * (size_t)c_plus_xyz * sizeof(float);
 }
@@ -287,19 +287,19 @@ extern "C" int gspn_ballquery_group(int b, int n, int m, int c, float radius, in
     GSPN_REQUIRE(radius > 0.f && nsample > 0);
     GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && c >= 0 && b <= 65535);
     if (points_dtype != GSPN_DT_F32 && points_dtype != GSPN_DT_BF16) return GSPN_E_BAD_DTYPE;
-    if (grouped_dtype != GSPN_DT_F32 && grouped_dtype != GSPN_DT_BF16) return GSPN_E_BAD_DTYPE;
+    if (grouped_dtype != GSPN_DT_F32 && grouped_dtype != GSPN_DT_BF16 && grouped_dtype != GSPN_DT_BF16X2) return GSPN_E_BAD_DTYPE;
     if (b == 0 || m == 0) return GSPN_OK;
     GSPN_REQUIRE_PTR(xyz); GSPN_REQUIRE_PTR(new_xyz); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(pts_cnt); GSPN_REQUIRE_PTR(grouped);
     if (c > 0) GSPN_REQUIRE_PTR(points);
     GSPN_REQUIRE(ld >= c + 3);
-    if (grouped_dtype == GSPN_DT_BF16) GSPN_REQUIRE(ld % 64 == 0);
+    if (grouped_dtype != GSPN_DT_F32) GSPN_REQUIRE(ld % 64 == 0);
     GroupArgs g;
     g.shift = shift;
     g.points = points;
     g.c = c;
     g.points_bf16 = points_dtype == GSPN_DT_BF16;
     g.grouped = grouped;
-    g.grouped_bf16 = grouped_dtype == GSPN_DT_BF16;
+    g.grouped_bf16 = grouped_dtype == GSPN_DT_BF16 ? 1 : (grouped_dtype == GSPN_DT_BF16X2 ? 2 : 0);
     g.ld = ld;
     if (workspace != nullptr && n >= kGridMinPoints && std::isfinite(radius)) {
         if (workspace_bytes < gspn_grid_workspace_bytes(b, n)) return GSPN_E_WORKSPACE;

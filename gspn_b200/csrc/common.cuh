@@ -73,16 +73,31 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 // 16-byte chunk c (8 bf16) lives at  (r/8)*1024 + (r%8)*128 + ((c ^ (r%8))*16)
 // -- exactly the K-major SWIZZLE_128B shared-memory layout tcgen05.mma reads, so a block
 // is moved HBM->smem by one 16 KiB cp.async.bulk with no tensor map.
+// SPLIT image (GSPN_DT_BF16X2, the bf16x3 arithmetic): every block is a PAIR [hi block | lo block] of 32 KiB, where
+// hi = bf16(x) and lo = bf16(x - hi); one 32 KiB cp.async.bulk moves both.
 constexpr int kTileRows = 128;
 constexpr int kTileCols = 64;
 constexpr int kTileBytes = kTileRows * kTileCols * 2;
 
-__host__ __device__ inline size_t tile_chunk_offset(long row, int col8 /* column / 8 */, int ld) {
+__host__ __device__ inline size_t tile_chunk_offset(long row, int col8 /* column / 8 */, int ld, int split = 0) {
     long t = row >> 7;
     int r = (int)(row & 127);
     int kb = col8 >> 3, c = col8 & 7;
-    return ((size_t)t * (size_t)(ld >> 6) + (size_t)kb) * (size_t)kTileBytes + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 +
+    return ((size_t)t * (size_t)(ld >> 6) + (size_t)kb) * (size_t)(kTileBytes << split) + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128 +
            (size_t)((c ^ (r & 7)) << 4);
 }
+
+#ifdef __CUDACC__
+// {low half = bf16(a), high half = bf16(b)}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+// split-bf16 pair of two floats: hi = bf16x2(a, b), lo = bf16x2(a - hi.a, b - hi.b); a == hi + lo to ~2^-17 relative
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(__fsub_rn(a, __uint_as_float(hi << 16)), __fsub_rn(b, __uint_as_float(hi & 0xffff0000u)));
+}
+#endif
 
 }  // namespace gspn

@@ -12,7 +12,7 @@ struct GroupArgs {
     int c;
     int points_bf16;
     void *grouped;  // null -> indices only
-    int grouped_bf16;
+    int grouped_bf16;  // 0: f32 rows, 1: bf16 tile image, 2: split (hi | lo) tile image (GSPN_DT_BF16X2)
     int ld;
 };
 
@@ -39,11 +39,6 @@ struct RowSrc {
         return 0.f;
     }
 };
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
 
 // write one neighbourhood (nsample rows) of query (cloud,j); sidx = the row's indices in smem.  The (row, column) space is swept by
 // `stride` threads of which this is number `lane`: one warp (lane, 32), or a whole CTA (threadIdx.x, blockDim.x).
@@ -72,28 +67,38 @@ __device__ __forceinline__ void write_group(const GroupArgs &g, int n, int m, in
         }
         return;
     }
-    // bf16 tile image: one 16-byte chunk (8 columns) per lane-step
+    // bf16 tile image: one 16-byte chunk (8 columns) per lane-step; the split image also gets the chunk of remainders
     unsigned char *img = (unsigned char *)g.grouped;
+    const int split = g.grouped_bf16 == 2;
     const int chunks = g.ld >> 3;
     const bool vec_f = src.pts_f && (g.c % 4 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_f) & 15u) == 0);
     const bool vec_h = src.pts_h && (g.c % 8 == 0) && ((reinterpret_cast<uintptr_t>(src.pts_h) & 15u) == 0);
     for (int e = lane; e < nsample * chunks; e += stride) {
         int s = e / chunks, ch = e - s * chunks;
         int ii = sidx[s];
-        uint4 pk;
+        uint4 pk, pl = make_uint4(0, 0, 0, 0);
         if (ch * 8 + 8 <= g.c && vec_h) {
-            pk = __ldg(reinterpret_cast<const uint4 *>(src.pts_h + (size_t)ii * g.c + ch * 8));
-        } else if (ch * 8 + 8 <= g.c && vec_f) {
-            const float4 *fp = reinterpret_cast<const float4 *>(src.pts_f + (size_t)ii * g.c + ch * 8);
-            float4 a = __ldg(fp), b = __ldg(fp + 1);
-            pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w); pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+            pk = __ldg(reinterpret_cast<const uint4 *>(src.pts_h + (size_t)ii * g.c + ch * 8));  // bf16 features: remainders are zero
         } else {
             float v[8];
+            if (ch * 8 + 8 <= g.c && vec_f) {
+                const float4 *fp = reinterpret_cast<const float4 *>(src.pts_f + (size_t)ii * g.c + ch * 8);
+                float4 a = __ldg(fp), b = __ldg(fp + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = src.at(ii, ch * 8 + t);
-            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+                for (int t = 0; t < 8; ++t) v[t] = src.at(ii, ch * 8 + t);
+            }
+            if (split) {
+                split_bf16x2(v[0], v[1], pk.x, pl.x); split_bf16x2(v[2], v[3], pk.y, pl.y);
+                split_bf16x2(v[4], v[5], pk.z, pl.z); split_bf16x2(v[6], v[7], pk.w, pl.w);
+            } else {
+                pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]); pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+            }
         }
-        *reinterpret_cast<uint4 *>(img + tile_chunk_offset(row0 + s, ch, g.ld)) = pk;
+        const size_t off = tile_chunk_offset(row0 + s, ch, g.ld, split);
+        *reinterpret_cast<uint4 *>(img + off) = pk;
+        if (split) *reinterpret_cast<uint4 *>(img + off + kTileBytes) = pl;
     }
 }
 

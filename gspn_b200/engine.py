@@ -7,10 +7,12 @@ while it runs.  Here a forward pass is captured once into a CUDA graph (no Pytho
 launch overhead on replay) and `depth` graphs on separate streams are kept in flight, so the FPS of
 batch i+1 overlaps the ball-query / tensor-core MLP / interpolation work of batch i.
 
-  eng = BackboneEngine(store, batch=8, npoints=32768, precision="bf16", depth=2)
+  eng = BackboneEngine(store, batch=8, npoints=32768, depth=2)          # result_dtype=torch.float32: the reference's output
   ticket = eng.submit(xyz, colour)        # device or pinned-host tensors; returns immediately
   feats = eng.result(ticket)              # (batch, npoints, 128) device tensor of that lane
   eng.result_to_host(ticket, pinned_out)  # async D2H on the lane's stream
+result_dtype=torch.float16 (serving form): the last chain's epilogue writes the per-point map as IEEE half ONLY (half the D2H bytes;
+each element within 2^-11 of the fp32 value, tests assert the 1e-3 bound on it).
 
 Results are identical to backbone.forward (same kernels, same order per batch).
 """
@@ -25,16 +27,16 @@ class _Lane:
         self.xyz = torch.zeros((batch, npoints, 3), dtype=torch.float32, device=dev)
         self.col = torch.zeros((batch, npoints, cin), dtype=torch.float32, device=dev)
         self.out = None
-        self.out_h = None  # bf16 copy of the feature map (bf16 path)
         self.graph = None
         self.done = torch.cuda.Event()
 
 
 class BackboneEngine:
-    def __init__(self, store, batch, npoints, precision="bf16", depth=2, use_graphs=True, colour_channels=3, device=None,
-                 sa_specs=backbone.SA_SPECS, fp_specs=backbone.FP_SPECS, warm_inputs=None):
+    def __init__(self, store, batch, npoints, precision=None, depth=2, use_graphs=True, colour_channels=3, device=None,
+                 sa_specs=backbone.SA_SPECS, fp_specs=backbone.FP_SPECS, warm_inputs=None, result_dtype=torch.float32):
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.store, self.precision = store, precision
+        self.result_dtype = result_dtype
         self.sa_specs, self.fp_specs = sa_specs, fp_specs
         self.use_graphs = use_graphs
         self.lanes = [_Lane(self.dev, batch, npoints, colour_channels) for _ in range(depth)]
@@ -44,18 +46,19 @@ class BackboneEngine:
                 lane.xyz.copy_(warm_inputs[0]); lane.col.copy_(warm_inputs[1])
             torch.cuda.synchronize(self.dev)
             with torch.cuda.stream(lane.stream):
-                lane.out, lane.out_h = self._forward(lane)  # eager warm-up: packs weights, folds BN, sets kernel attributes
+                lane.out = self._forward(lane)  # eager warm-up: packs weights, folds BN, sets kernel attributes
             lane.stream.synchronize()
             if use_graphs:
                 lane.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(lane.graph, stream=lane.stream, capture_error_mode="relaxed"):
-                    lane.out, lane.out_h = self._forward(lane)
+                    lane.out = self._forward(lane)
         torch.cuda.synchronize(self.dev)
 
     def _forward(self, lane):
+        half = None if self.result_dtype == torch.float32 else self.result_dtype
         r = backbone.forward(lane.xyz, lane.col, self.store, sa_specs=self.sa_specs, fp_specs=self.fp_specs,
-                             precision=self.precision, l0_bf16=True)
-        return r["l0_points"], r.get("l0_points_bf16")
+                             precision=self.precision, l0_half=half, l0_f32=half is None)
+        return r["l0_points"] if half is None else r["l0_points_half"]
 
     def submit(self, xyz, colour, after=None):
         """Enqueue one batch on the next lane. xyz/colour: device tensors or pinned host tensors."""
@@ -70,7 +73,7 @@ class BackboneEngine:
             if lane.graph is not None:
                 lane.graph.replay()
             else:
-                lane.out, lane.out_h = self._forward(lane)
+                lane.out = self._forward(lane)
             lane.done.record(lane.stream)
         return i
 
@@ -78,11 +81,11 @@ class BackboneEngine:
         return self.lanes[ticket].out
 
     def result_to_host(self, ticket, pinned_out):
-        """Async D2H of the lane's feature map on the lane's stream; a bfloat16 `pinned_out` takes the bf16 map."""
+        """Async D2H of the lane's feature map (result_dtype) on the lane's stream."""
         lane = self.lanes[ticket]
-        src = lane.out_h if (pinned_out.dtype == torch.bfloat16 and lane.out_h is not None) else lane.out
+        assert pinned_out.dtype == lane.out.dtype, "pinned_out must have the engine's result_dtype"
         with torch.cuda.stream(lane.stream):
-            pinned_out.copy_(src, non_blocking=True)
+            pinned_out.copy_(lane.out, non_blocking=True)
             lane.done.record(lane.stream)
 
     def join(self, onto=None):

@@ -22,7 +22,7 @@ Shape errors raise ValueError carrying the reference's OP_REQUIRES message.
 import torch
 
 from . import _lib
-from ._lib import GSPN_DT_BF16, GSPN_DT_F32, check
+from ._lib import GSPN_DT_BF16, GSPN_DT_BF16X2, GSPN_DT_F32, check
 
 
 def _stream():
@@ -305,8 +305,9 @@ def ballquery_group(radius, nsample, xyz, new_xyz, points, grouped_dtype=torch.f
     (utils/pointnet_util.py:40-48).  Returns (idx, pts_cnt, grouped, ld).
 
     grouped rows are [features(c) | xyz-centre(3) | 0-pad]  (features FIRST; callers permute the
-    first layer's weight rows accordingly).  float32: a (b*m*nsample, ld=c+3) tensor; bfloat16:
-    the 128B-swizzled tile image for mlp_chain (uint8 buffer), ld = 64*ceil((c+3)/64)."""
+    first layer's weight rows accordingly).  grouped_dtype: torch.float32 -> a (b*m*nsample, ld=c+3) tensor;
+    torch.bfloat16 / "image:bf16" -> the 128B-swizzled bf16 tile image for mlp_chain (uint8 buffer), ld = 64*ceil((c+3)/64);
+    "image:bf16x3" -> the same image with every block a [hi | lo] pair (split-bf16 arithmetic)."""
     _req(radius > 0, "QueryBallPoint expects positive radius")
     _req(nsample > 0, "QueryBallPoint expects positive nsample")
     xyz, new_xyz = _cuda_f32(xyz.detach(), "xyz"), _cuda_f32(new_xyz.detach(), "new_xyz")
@@ -327,13 +328,15 @@ def ballquery_group(radius, nsample, xyz, new_xyz, points, grouped_dtype=torch.f
     rows = b * m * nsample
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz.device)
     cnt = torch.empty((b, m), dtype=torch.int32, device=xyz.device)
-    if grouped_dtype == torch.bfloat16:
-        gdt = GSPN_DT_BF16
+    if grouped_dtype in (torch.bfloat16, "image:bf16", "image:bf16x3"):
+        gdt = GSPN_DT_BF16X2 if grouped_dtype == "image:bf16x3" else GSPN_DT_BF16
         ld = ((c + 3 + 63) // 64) * 64
         nbytes = L.gspn_grouped_bytes(rows, c + 3, gdt)
         grouped = torch.empty((nbytes,), dtype=torch.uint8, device=xyz.device)
         if rows % 128:
-            grouped[-(ld // 64) * 16384:].zero_()  # rows of the last tile that no query owns
+            grouped[-(ld // 64) * 16384 * (2 if gdt == GSPN_DT_BF16X2 else 1):].zero_()  # rows of the last tile that no query owns
+    elif grouped_dtype != torch.float32:
+        raise TypeError("grouped_dtype must be torch.float32, torch.bfloat16, 'image:bf16' or 'image:bf16x3'")
     else:
         gdt = GSPN_DT_F32
         ld = c + 3

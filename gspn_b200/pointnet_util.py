@@ -12,10 +12,13 @@ The reference builds a TF graph whose variables live in TF's variable store unde
 Here `scope` keys a `VariableStore` (a dict of per-layer tensors named like the TF variables:
 <scope>/conv<i>/{weights,biases,bn/gamma,bn/beta,bn/moving_mean,bn/moving_variance}); the first call
 under a scope creates the variables (Xavier-uniform weights, zero biases, identity BN) exactly as
-tf.get_variable would, later calls reuse them.  Two execution precisions share every index op:
+tf.get_variable would, later calls reuse them.  Three execution precisions share every index op:
 
-  precision='fp32' : reference-precision MLP on CUDA cores (parity tolerance 1e-5),
-  precision='bf16' : tcgen05 tensor-core MLP chain fed by the fused ball-query+group tile image.
+  precision='bf16x3' (default): tcgen05 tensor-core MLP chain in split-bf16 arithmetic (hi*hi + lo*hi + hi*lo into the fp32
+                     accumulator, ~2^-16): within 1e-3 of the reference's fp32 results (tests assert 1e-3, measured ~1e-5),
+  precision='bf16' : the same chain with one bf16 product per term (what BASELINE.json's north_star names; unit round-off 2^-8,
+                     so 5e-3 .. 3e-2 away from the fp32 reference -- OUTSIDE its 1e-3 bound; opt-in),
+  precision='fp32' : reference-precision MLP on CUDA cores (parity tolerance 1e-5).
 
 is_training=True runs the fp32 training form (gspn_b200/train.py): batch-statistics batch norm with in-place moving
 average updates, autograd through MLP, max-pool, grouping and interpolation.
@@ -30,7 +33,8 @@ from . import ops
 
 BN_EPS = 1e-3  # tf.contrib.layers.batch_norm default epsilon (utils/tf_util.py:530-534)
 
-DEFAULT_PRECISION = "bf16"  # the north-star path (tcgen05); pass precision="fp32" for reference-precision MLPs
+DEFAULT_PRECISION = "bf16x3"  # tcgen05 chain, split-bf16 arithmetic: meets the 1e-3 float bound.  "bf16" and "fp32" are opt-in
+TC_PRECISIONS = ("bf16x3", "bf16")
 
 
 class VariableStore(dict):
@@ -147,6 +151,15 @@ def _run_mlp_f32(x2d, layers, pool_last=1):
     return x2d
 
 
+def _pool_only(grouped, nsample, c, use_xyz, has_points):
+    """mlp == []: tf.reduce_max of the grouped rows themselves, columns back in the reference's order [xyz | features]
+    (pointnet_util.py:48,124); the fused grouping kernel writes [features | xyz]."""
+    x = ops.mlp_pool(grouped, nsample)
+    if not has_points:
+        return x
+    return torch.cat([x[:, c:c + 3], x[:, :c]], dim=1).contiguous() if use_xyz else x[:, :c].contiguous()
+
+
 def _features_first(layer, c, use_xyz, has_points):
     """First-layer dict whose kernel rows are re-ordered for the fused grouping layout [features | xyz]
     (reference order is [xyz | features], pointnet_util.py:48).  Cached on the layer dict."""
@@ -194,9 +207,11 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
         with _stage(timers, scope + ":gather"):
             new_xyz = ops.gather_point(xyz, fps_idx)
         m = npoint
-        if precision == "bf16":
+        if precision in TC_PRECISIONS:
             from . import mlp_tc
-            idx, x = mlp_tc.sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz, store, scope, timers)
+            idx, x = mlp_tc.sa_group_mlp_max(xyz, new_xyz, points, radius, nsample, layers, use_xyz, store, scope, timers, precision)
+        elif precision != "fp32":
+            raise ValueError("precision must be one of 'bf16x3', 'bf16', 'fp32'")
         else:
             with _stage(timers, scope + ":ballquery_group"):
                 idx, _, grouped, _ = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
@@ -205,15 +220,16 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
                     first = _features_first(layers[0], c, use_xyz, points is not None)
                     x = _run_mlp_f32(grouped, [first] + list(layers[1:]), pool_last=nsample)
                 else:
-                    x = ops.mlp_pool(grouped, nsample)
+                    x = _pool_only(grouped, nsample, c, use_xyz, points is not None)
     x = _run_mlp_f32(x, layers2)
     return new_xyz, x.reshape(b, m, x.shape[-1]), idx
 
 
 def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay, scope, bn=True, reuse=False, variables=None,
-                       precision=None, timers=None, also_bf16=False):
+                       precision=None, timers=None, half_output=None, f32_output=True):
     """-> new_points1 (b,n,mlp[-1])  (or the concatenated (b,n,c2+c1) map when mlp == []).
-    also_bf16 (extension, bf16 path only): return (f32 map, bf16 map) -- the tensor-core chain emits both."""
+    half_output (extension, tensor-core paths): torch.float16 / torch.bfloat16 -> return (f32 map, 16-bit map), the chain's epilogue
+    emits the copy; f32_output=False then skips the fp32 map (returns (None, 16-bit map))."""
     _check_unbuilt(is_training)
     store = VARIABLES if variables is None else variables
     precision = precision or DEFAULT_PRECISION
@@ -226,9 +242,12 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
         return train.fp_module_train(xyz1, xyz2, points1, points2, layers, bn_decay)
     with _stage(timers, scope + ":three_nn"):
         _, idx, weight = ops.three_nn(xyz1, xyz2, return_weight=True)
-    if precision == "bf16" and layers:
+    if precision in TC_PRECISIONS and layers:
         from . import mlp_tc
-        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers, want_bf16=also_bf16)
+        return mlp_tc.fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers, precision, want_half=half_output,
+                                    want_f32=f32_output or half_output is None)
+    if precision not in TC_PRECISIONS and precision != "fp32":
+        raise ValueError("precision must be one of 'bf16x3', 'bf16', 'fp32'")
     with _stage(timers, scope + ":interpolate"):
         interpolated = ops.three_interpolate(points2, idx, weight)
         new_points1 = torch.cat([interpolated, points1], dim=2) if points1 is not None else interpolated
@@ -236,4 +255,5 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp, is_training, bn_decay,
         return new_points1
     with _stage(timers, scope + ":mlp"):
         x = _run_mlp_f32(new_points1.reshape(b * n, c1 + c2), layers)
-    return x.reshape(b, n, x.shape[-1])
+    x = x.reshape(b, n, x.shape[-1])
+    return (x, x.to(half_output)) if half_output is not None else x

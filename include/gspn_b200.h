@@ -42,7 +42,13 @@ enum {
     GSPN_E_UNSUPPORTED = -6  /* valid request outside what this build implements */
 };
 
-enum { GSPN_DT_F32 = 0, GSPN_DT_BF16 = 1 };
+/* element / image types: F32 and BF16 rows or tile images; BF16X2 = the split tile image of the bf16x3 arithmetic (every block a
+ * [hi | lo] pair with hi = bf16(x), lo = bf16(x - hi)); F16 = IEEE half (16-bit output copy only). */
+enum { GSPN_DT_F32 = 0, GSPN_DT_BF16 = 1, GSPN_DT_BF16X2 = 2, GSPN_DT_F16 = 3 };
+/* arithmetic of the tensor-core MLP chain.  BF16: one bf16 x bf16 product per term (unit round-off 2^-8; what north_star names).
+ * BF16X3: split-bf16 -- operands carried as hi + lo bf16 pairs, a*b accumulated as hi*hi + lo*hi + hi*lo in the fp32 accumulator
+ * (three tcgen05.mma per k-slice, error ~2^-16): the mode that keeps the MLP inside the reference's fp32 results to 1e-3. */
+enum { GSPN_MLP_BF16 = 0, GSPN_MLP_BF16X3 = 1 };
 
 /* Human-readable text for a GSPN_E_* code (static storage). */
 const char *gspn_error_string(int code);
@@ -111,7 +117,8 @@ int gspn_group_point_grad(int b, int n, int c, int m, int nsample, const float *
  * `points` may be NULL (c=0).  shift (b,m,3) may be NULL.  grouped_dtype selects
  *   GSPN_DT_F32 : plain row-major (b*m*nsample, ld) float rows, ld >= c+3;
  *   GSPN_DT_BF16: the tensor-core-ready tile image consumed by gspn_mlp_chain
- *                 (128-row x 64-col bf16 blocks, 128B-swizzled, ld = 64*ceil((c+3)/64)).
+ *                 (128-row x 64-col bf16 blocks, 128B-swizzled, ld = 64*ceil((c+3)/64));
+ *   GSPN_DT_BF16X2: the same with every block stored as a [hi | lo] pair (GSPN_MLP_BF16X3 arithmetic).
  * points_dtype is the dtype of `points` (f32 as in the reference, or bf16 as
  * produced by gspn_mlp_chain). */
 size_t gspn_grouped_bytes(long rows, int c_plus_xyz, int grouped_dtype);
@@ -169,26 +176,41 @@ int gspn_mlp_layer_f32(long rows, int cin, int cout, const float *x, int ldx, co
 /* tf.reduce_max over groups of k consecutive rows: x (groups*k, c) -> y (groups, c)  (pointnet_util.py:124). */
 int gspn_max_pool_rows(long groups, int k, int c, const float *x, float *y, gspn_stream_t stream);
 
-/* bf16 tensor-core path (tcgen05 / TMEM), whole chain in one kernel.
- *   a       : tile image from gspn_ballquery_group / gspn_fp_assemble (rows padded to 128)
- *   nlayers : 1..4;  dims[0]=K0 (multiple of 64, as `ld` above), dims[l+1]=cout of layer l
- *   wimg[l] : weight image from gspn_mlp_pack_weights; scale/shift as above (f32, cout_l)
- *   pool    : 1 (no pooling) or a divisor of 128 (nsample) or a multiple of 128
- *   out_f32 (rows/pool, cout_last) and/or out_bf16 (same shape, row-major bf16) may be NULL. */
-size_t gspn_mlp_weight_image_bytes(int cin_padded, int cout);
+/* Tensor-core path (tcgen05 / TMEM), whole chain in one kernel (csrc/mlp_tc.cu); `arith` = GSPN_MLP_BF16 or GSPN_MLP_BF16X3.
+ *   a       : tile image from gspn_ballquery_group / gspn_fp_assemble (rows padded to 128); GSPN_DT_BF16 image for GSPN_MLP_BF16,
+ *             GSPN_DT_BF16X2 image for GSPN_MLP_BF16X3
+ *   nlayers : 1..4;  dims[0]=K0 (multiple of 64, as `ld` above), dims[l+1]=cout of layer l (multiples of 32, <= 512; hidden
+ *             widths <= 256); k0_used = columns of the image that hold data (0: all K0) -- only those k-slices are multiplied
+ *   wimg[l] : weight image from gspn_mlp_pack_weights (same arith); scale/shift as above (f32, cout_l)
+ *   pool    : 1 (no pooling) or a multiple of 32 dividing rows (nsample)
+ *   out_f32 (rows/pool, cout_last) and/or out_h (same shape, row-major, out_h_dtype = GSPN_DT_BF16 or GSPN_DT_F16 with
+ *   saturation to the finite half range) may be NULL. */
+size_t gspn_mlp_weight_image_bytes(int cin_padded, int cout, int arith);
 int gspn_mlp_pack_weights(int cin, int cin_padded, int cout, const float *w_f32, const int *row_perm,
-                          void *wimg, gspn_stream_t stream);
-int gspn_mlp_chain(long rows, int nlayers, const int *dims, const void *a,
+                          void *wimg, int arith, gspn_stream_t stream);
+int gspn_mlp_chain(long rows, int nlayers, const int *dims, int k0_used, const void *a,
                    const void *const *wimg, const float *const *scale, const float *const *shift,
-                   const int *relu, int pool, float *out_f32, void *out_bf16, gspn_stream_t stream);
+                   const int *relu, int pool, float *out_f32, void *out_h, int out_h_dtype, int arith, gspn_stream_t stream);
 
 /* Same chain, but layer 0's operand rows [points[b,idx,:c] | xyz[b,idx]-new_xyz[b,j]-shift[b,j] | 0] (c+3 <= 8, dims[0]=64) are
- * gathered by the kernel's producer warp straight from the ball-query indices idx (b,m,nsample): the grouped tensor of
+ * gathered by the kernel's producer warps straight from the ball-query indices idx (b,m,nsample): the grouped tensor of
  * sample_and_group (utils/pointnet_util.py:40-48) is never written to HBM.  Same values as gspn_ballquery_group + gspn_mlp_chain. */
 int gspn_mlp_chain_gather(int b, int n, int m, int nsample, int c, const float *xyz, const float *new_xyz, const float *shift_pred,
                           const float *points, const int *idx, int nlayers, const int *dims, const void *const *wimg,
                           const float *const *scale, const float *const *shift, const int *relu, int pool,
-                          float *out_f32, void *out_bf16, gspn_stream_t stream);
+                          float *out_f32, void *out_h, int out_h_dtype, int arith, gspn_stream_t stream);
+
+/* pointnet_fp_module's interpolate + concat + MLP (utils/pointnet_util.py:156-172) with the interpolated map never written:
+ * three_interpolate is linear, so  concat(interp3(points2), points1) @ W0 = interp3(points2 @ W0[:c2]) + points1 @ W0[c2:].
+ * The caller multiplies the m known points once (y2 = points2 @ W0[:c2], (b,m,n0) f32, e.g. a one-layer gspn_mlp_chain with scale 1 /
+ * shift 0 / no ReLU); the kernel's producer warps gather the three rows of y2 per point, finish layer 0 on the CUDA cores
+ * (act(scale[0] * (w1*y2[i1] + w2*y2[i2] + w3*y2[i3] + points1 @ w0b) + shift[0])) and feed layers 1.. to the tensor cores.
+ *   idx / weight (b,n,3) from gspn_three_nn; points1 (b,n,c1) with c1 <= 4, or NULL; w0b = W0[c2:] (c1,n0) f32
+ *   nlayers >= 2 counts layer 0; dims[0] ignored, dims[1] = n0 (multiple of 64), dims[l+1] = cout of layer l; wimg[0] unused. */
+int gspn_mlp_chain_fp(int b, int n, int m, int c1, const float *y2, const int *idx, const float *weight, const float *points1,
+                      const float *w0b, int nlayers, const int *dims, const void *const *wimg, const float *const *scale,
+                      const float *const *shift, const int *relu, float *out_f32, void *out_h, int out_h_dtype, int arith,
+                      gspn_stream_t stream);
 
 /* ---- training form of the shared MLP (fp32): conv 1x1 + bias -> batch norm over the BATCH moments
  * (tf.contrib.layers.batch_norm, is_training=True, utils/tf_util.py:515-534) -> ReLU -> reduce_max, and its backward.
@@ -214,16 +236,21 @@ int gspn_mlp_wgrad_f32(long rows, int cin, int cout, const float *x, int ldx, co
 int gspn_group_rows_grad(int b, int n, int c, int m, int nsample, int ld, const float *grad_rows, const int *idx,
                          float *grad_points, gspn_stream_t stream);
 
-/* Tuning door: when prof (device, 16 x int64, zeroed by the caller) is non-NULL, later gspn_mlp_chain launches add CTA 0's
- * cycle counts: epilogue thread 0: [1] wait for the MMAs, [2] epilogue, [3] fences+hand-off, [4] number of layer-steps;
- * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands, [7] operand + hand-off waits.  NULL switches it off. */
-void gspn_mlp_chain_set_profile(long long *prof5);
+/* Tuning doors (benchmark A/B runs; process-wide, NOT thread-safe, nothing is read from the environment).
+ * gspn_mlp_chain_set_profile: when prof (device, 16 x int64, zeroed by the caller) is non-NULL, later chain launches add CTA 0's
+ * cycle counts: epilogue thread 0: [1] wait for the MMAs, [2] epilogue, [3] fences+hand-off, [4] number of steps;
+ * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands, [7] hand-off waits.  NULL switches it off.
+ * gspn_mlp_chain_tune: occ_cap 1|2 = most chain CTAs per SM, bufs_cap 1|2 = most TMEM accumulator buffers,
+ * tma_out 0 = row-per-lane 256-bit output stores instead of TMA tensor stores.  Defaults (2, 2, 1) are the measured best. */
+void gspn_mlp_chain_set_profile(long long *prof);
+void gspn_mlp_chain_tune(int occ_cap, int bufs_cap, int tma_out);
 
 /* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of
  * points2 (b,m,c2) with idx/weight (b,n,3), concatenated with points1 (b,n,c1) (may be NULL, c1=0),
- * written straight into the bf16 tile image (ld = 64*ceil((c1+c2)/64)) for gspn_mlp_chain. */
+ * written straight into the tile image (ld = 64*ceil((c1+c2)/64); image_dtype GSPN_DT_BF16 or GSPN_DT_BF16X2) for gspn_mlp_chain.
+ * c2 = 0 (points2, idx, weight NULL): plain rows points1 -> tile image. */
 int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float *points1, const float *points2,
-                     const int *idx, const float *weight, void *a_img, int ld, gspn_stream_t stream);
+                     const int *idx, const float *weight, void *a_img, int ld, int image_dtype, gspn_stream_t stream);
 
 /* ---- brute-force nearest-neighbour glue around the path ------------------------------
  * One-directional 1-NN: for every query (b,n,3) the nearest reference point (b,m,3): squared distance dist (b,n)

@@ -1,6 +1,6 @@
 """Throughput ablations of the pipelined executor: what does a stage cost the STEP (not its own kernel time)?
 Replaces one op family by a cached result before the graphs are captured and re-measures ms/step; also sweeps the
-number of graph lanes.  Run under gpurun.   usage: python tools/ablate.py [depth]"""
+number of graph lanes.  Run under gpurun.   usage: python tools/ablate.py [depth [precision]]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,6 +10,7 @@ from gspn_b200.engine import BackboneEngine
 dev = torch.device("cuda:0")
 B, N, STEPS = 8, 32768, 32
 DEPTH = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+PREC = sys.argv[2] if len(sys.argv) > 2 else None  # None = the default precision (bf16x3)
 batches = []
 for i in range(6):
     xyz, col = scenes.scannet_like_batch(i * B, B, N)
@@ -18,7 +19,7 @@ store, _ = backbone.random_variables(dev)
 
 
 def measure(tag, depth=DEPTH):
-    eng = BackboneEngine(store, B, N, precision="bf16", depth=depth, device=dev, warm_inputs=batches[0])
+    eng = BackboneEngine(store, B, N, precision=PREC, depth=depth, device=dev, warm_inputs=batches[0])
     for w in range(depth):
         eng.submit(*batches[w % 6])
     eng.synchronize()
@@ -59,8 +60,8 @@ ops.farthest_point_sample = cached(real["fps"], lambda npoint, inp: (npoint, shp
 measure("without FPS level 1")
 ops.farthest_point_sample = cached(real["fps"], lambda npoint, inp: (npoint, shp(inp)))
 measure("without any FPS")
-mlp_tc.mlp_chain = cached(real["chain"], lambda a_img, rows, k0, layers, first_perm, pool, want_bf16=False: (rows, k0, pool, want_bf16))
-mlp_tc.mlp_chain_gather = cached(real["chain_g"], lambda xyz, new_xyz, shift, points, idx, layers, first_perm, pool: (shp(idx), pool))
+mlp_tc.mlp_chain = cached(real["chain"], lambda a_img, rows, k0, layers, first_perm, pool, precision="bf16x3", k0_used=0, want_half=None, want_f32=True, relus=None: (rows, k0, pool, precision, want_half, want_f32))
+mlp_tc.mlp_chain_gather = cached(real["chain_g"], lambda xyz, new_xyz, shift, points, idx, layers, first_perm, pool, precision="bf16x3": (shp(idx), pool, precision))
 measure("without FPS and MLP chains")
 ops.farthest_point_sample = real["fps"]
 measure("without MLP chains")

@@ -11,7 +11,7 @@ x, c = torch.from_numpy(xyz).to(dev), torch.from_numpy(col).to(dev)
 specs = backbone.scaled_sa_specs(4608)
 store, _ = backbone.random_variables(dev, sa_specs=specs)
 for prec in ("bf16", "fp32"):
-    out = backbone.forward(x, c, store, sa_specs=specs, precision=prec, l0_bf16=True)
+    out = backbone.forward(x, c, store, sa_specs=specs, precision=prec, l0_half=torch.float16)
 torch.cuda.synchronize()
 fps = gspn_b200.farthest_point_sample(16, x)
 context_encoder.multi_encoding_net(x, c, 16, [0.5, 1.0], [64, 128], [[64, 128, 256]] * 2, [], False, None, "ctx", use_xyz=True, fps_idx=fps,

@@ -7,6 +7,7 @@ from gspn_b200 import _lib, mlp_tc
 import test_gpu_parity as tp
 dev = torch.device("cuda:0")
 L = _lib.lib()
+PREC = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 for name, rows, cin, widths, pool in [("sa1", 8 * 2048 * 32, 6, [32, 32, 64], 32), ("sa2", 8 * 512 * 32, 67, [64, 64, 128], 32),
                                       ("sa4", 8 * 32 * 32, 259, [256, 256, 512], 32), ("fp4", 8 * 32768, 131, [128, 128, 128], 1),
                                       ("fp1", 8 * 128, 768, [256, 256], 1)]:
@@ -15,15 +16,15 @@ for name, rows, cin, widths, pool in [("sa1", 8 * 2048 * 32, 6, [32, 32, 64], 32
     tl = [{k: tp.T(v, dev) for k, v in l.items()} for l in layers]
     ld = ((cin + 63) // 64) * 64
     tiles = (rows + 127) // 128
-    img = torch.zeros(tiles * (ld // 64) * 16384, dtype=torch.uint8, device=dev)
-    mlp_tc.mlp_chain(img, rows, ld, tl, None, pool)
+    img = torch.zeros(tiles * (ld // 64) * 16384 * (2 if PREC == "bf16x3" else 1), dtype=torch.uint8, device=dev)
+    mlp_tc.mlp_chain(img, rows, ld, tl, None, pool, PREC, k0_used=cin)
     prof = torch.zeros(16, dtype=torch.int64, device=dev)
     L.gspn_mlp_chain_set_profile(prof.data_ptr())
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); mlp_tc.mlp_chain(img, rows, ld, tl, None, pool); b.record()
+    a.record(); mlp_tc.mlp_chain(img, rows, ld, tl, None, pool, PREC, k0_used=cin); b.record()
     torch.cuda.synchronize()
     L.gspn_mlp_chain_set_profile(None)
     p = prof.cpu().numpy().astype(float)
     n = max(p[4], 1)
-    print("%-4s rows %7d kernel+launch %.3f ms | per layer-step cycles: issue %.0f mma_wait %.0f epilogue %.0f sync %.0f (steps %d) | MMA thread: wait %.0f issue %.0f drain %.0f" %
+    print(PREC + " %-4s rows %7d kernel+launch %.3f ms | per layer-step cycles: issue %.0f mma_wait %.0f epilogue %.0f sync %.0f (steps %d) | MMA thread: wait %.0f issue %.0f drain %.0f" %
           (name, rows, a.elapsed_time(b), p[0] / n, p[1] / n, p[2] / n, p[3] / n, int(p[4]), p[7] / n, p[5] / n, p[6] / n), flush=True)
