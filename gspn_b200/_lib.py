@@ -28,10 +28,13 @@ SIGNATURES = {
     "gspn_error_string": (ctypes.c_char_p, [c_int]),
     "gspn_version": (c_int, []),
     "gspn_last_cuda_error": (ctypes.c_char_p, []),
+    "gspn_fp32_peak_probe": (c_int, [c_int, c_int, P, P, P]),
     "gspn_farthest_point_sample_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gspn_fps_max_resident_points": (c_int, []),
     "gspn_farthest_point_sample": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "gspn_farthest_point_sample_cfg": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P]),
+    "gspn_fps_tune": (None, [c_int]),
+    "gspn_fps_bucket_profile": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P, P]),
     "gspn_fps_profile": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P]),
     "gspn_gather_point": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_gather_point_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),

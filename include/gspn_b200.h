@@ -57,15 +57,24 @@ int gspn_version(void);
 /* cudaGetErrorString of the last GSPN_E_CUDA seen by the calling thread. */
 const char *gspn_last_cuda_error(void);
 
+/* Measurement aid (bench.py): launches `blocks` x 256 threads of `iters` x 16 independent FFMA each on `stream` and writes the
+ * flop count of the launch to *flops_out (host); timing it gives the FP32 FMA rate the search kernels' "pair evaluations / s"
+ * roofline is quoted against.  scratch: one device float. */
+int gspn_fp32_peak_probe(int blocks, int iters, float *scratch, double *flops_out, gspn_stream_t stream);
+
 /* ------------------------------------------------------------------ sampling
  * farthest_point_sample(npoint, inp)  tf_ops/sampling/tf_sampling.py:48-56
  *   FarthestPointSampleGpuOp::Compute  tf_ops/sampling/tf_sampling.cpp:95-122
  *   farthestpointsamplingLauncher(b,n,m,inp,temp,out)  tf_sampling_g.cu:203
  * inp (b,n,3) f32 -> out (b,m) i32, bit-identical to the reference kernel
- * (out[:,0]=0; ties -> lowest (k mod 512, k)).  The reference's temp (32,n)
- * scratch is not needed: clouds up to gspn_fps_max_resident_points() (131072) live entirely in registers, up to
- * 524288 points a 16-CTA cluster keeps the distances in registers and streams coordinates from L2; only above that
- * pass workspace of gspn_farthest_point_sample_workspace_bytes(b,n,m) for the single-CTA fallback. */
+ * (out[:,0]=0; ties -> lowest (k mod 512, k)).  The reference's temp (32,n) scratch is not needed.  Kernels by cloud size:
+ *   up to 131072 points (gspn_fps_max_resident_points()): register-resident cluster kernels (csrc/fps.cu), no workspace; up to
+ *   524288 a 16-CTA cluster keeps the distances in registers and streams coordinates from L2; above that the single-CTA fallback
+ *   needs workspace.  Opt-in, after gspn_fps_tune(1), for 8193 .. 32768 points with workspace: the exact bucket-pruned single-CTA
+ *   kernel (csrc/fps_bucket.cu: the cloud sorted into spatial buckets, resident in shared memory + tensor memory + registers of ONE
+ *   SM; a round only updates the buckets the new sample can reach -- same indices, 80x fewer distance evaluations, one SM instead
+ *   of eight, but measured slower per cloud, so it is not the default).
+ * Pass workspace of gspn_farthest_point_sample_workspace_bytes(b,n,m) bytes (0 when none is used). */
 size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m);
 int gspn_fps_max_resident_points(void);
 int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out,
@@ -74,6 +83,14 @@ int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out,
  * CTAs per cluster); 0 = choose.  Same results for every legal choice. */
 int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *out,
                                    int threads, int ppt, int cluster, gspn_stream_t stream);
+
+/* Tuning doors (process-wide, not thread-safe).  gspn_fps_tune(1) switches the bucket-pruned kernel on (default 0: full-scan
+ * kernels for every size).  gspn_fps_bucket_profile runs the bucket kernel and writes for cloud 0: prof3[0] = SM cycles of the round loop,
+ * prof3[1] = rounds, prof3[2] = bucket updates, prof3[3..7] = warp 0's cycles in: box tests, bucket updates, warp argmax, barrier
+ * wait, table reduce, prof3[8] = bucket updates that needed the full argmax (prof3: 12 x int64, zeroed by the caller). */
+void gspn_fps_tune(int use_buckets);
+int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
+                            long long *prof3, gspn_stream_t stream);
 
 /* Tuning door: per-phase SM-cycle counts of thread 0 of cloud 0, summed over the m-1 rounds:
  * prof4[0..3] = distance update + argmax, warp reduce, candidate exchange, table reduce. */

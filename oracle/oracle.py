@@ -224,6 +224,23 @@ def mlp_layer(x, layer, relu=True):
     return y.reshape(shp[:-1] + (cout,))
 
 
+def mlp_layer_blas(x, layer, relu=True):
+    """The same layer with the matrix product done by a BLAS-class fp32 GEMM (torch CPU matmul -> MKL/oneDNN sgemm): the stand-in
+    for what TensorFlow-CPU (Eigen contraction) would run, used by bench.py's reference arm / cpu_baseline (TensorFlow itself is not
+    installable here).  mlp_layer above (naive loop, strict left-to-right fp32) stays the CHECKER."""
+    import torch
+    x = _f32(x)
+    shp = x.shape
+    w = torch.from_numpy(_f32(layer["weights"]))
+    y = torch.from_numpy(x.reshape(-1, shp[-1])) @ w + torch.from_numpy(_f32(layer["biases"]))
+    if layer.get("gamma") is not None:
+        g, be, mu, var = (torch.from_numpy(_f32(layer[k])) for k in ("gamma", "beta", "moving_mean", "moving_variance"))
+        y = (y - mu) * (g / torch.sqrt(var + 1e-3)) + be
+    if relu:
+        y = torch.relu_(y)
+    return y.numpy().reshape(shp[:-1] + (w.shape[1],))
+
+
 def max_over_k(x):
     """tf.reduce_max(new_points, axis=[2]) (pointnet_util.py:124)."""
     x = _f32(x)

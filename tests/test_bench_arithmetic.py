@@ -29,14 +29,20 @@ def test_search_and_gather_bytes():
     n, m, k = 32768, 2048, 32
     # FPS: B*(12n + 4m); SA1 in the bf16 path gathers inside the chain, so its search stage moves the cloud, the queries and
     # writes idx / pts_cnt only
-    assert bf["layer1:fps"] == ("hbm", 8 * (12 * n + 4 * m))
-    assert bf["layer1:ballquery_group"] == ("hbm", 8 * (12 * n + 12 * m + 4 * m * k + 4 * m))
+    assert bf["layer1:fps"][:2] == ("hbm", 8 * (12 * n + 4 * m))
+    assert bf["layer1:ballquery_group"][:2] == ("hbm", 8 * (12 * n + 12 * m + 4 * m * k + 4 * m))
+    # pair evaluations of the reference's scans: FPS B*(m-1)*n, ball query / three_nn B*n*m
+    assert bf["layer1:fps"][2] == 8 * (m - 1) * n and bf["layer1:ballquery_group"][2] == 8 * m * n and bf["fa_layer4:three_nn"][2] == 8 * n * m
     # fp32 path: the grouped (m, K, 3 + C) rows are written as fp32 (SURVEY.md 8(d) formula with e_out = 4, ld = c + 3)
     assert f32["layer1:ballquery_group"][1] == 8 * (12 * n + 12 * m + n * 3 * 4 + 4 * m * k + 4 * m + m * k * 6 * 4)
     # SA2 (C = 64): tile image of ld = 128 bf16 columns
     assert bf["layer2:ballquery_group"][1] == 8 * (12 * 2048 + 12 * 512 + 2048 * 64 * 4 + 4 * 512 * 32 + 4 * 512 + 512 * 32 * 128 * 2)
     # three_nn FP4: B*(12n + 12m + 36n)
-    assert bf["fa_layer4:three_nn"] == ("hbm", 8 * (12 * n + 12 * m + 36 * n))
+    assert bf["fa_layer4:three_nn"][:2] == ("hbm", 8 * (12 * n + 12 * m + 36 * n))
+    # the split image of the default precision stores a [hi | lo] pair per element: 4 bytes
+    x3 = b.stage_costs(8, "bf16x3")
+    assert x3["layer2:ballquery_group"][1] - bf["layer2:ballquery_group"][1] == 8 * 512 * 32 * 128 * 2
+    assert x3["layer1:mlp"] == bf["layer1:mlp"]
 
 
 def test_peaks_loader_prefers_measured_file(tmp_path, monkeypatch):

@@ -89,6 +89,41 @@ def test_fps_full_size_config2(cuda, oracle):
     assert all(a >= b * (1 - 1e-6) for a, b in zip(sel, sel[1:]))
 
 
+FPS_BUCKET_CASES = [
+    ("scene_16384", lambda: scenes.scannet_like_batch(3, 3, 16384)[0], 700),
+    ("n8193_smallest", lambda: scenes.scannet_like_batch(4, 2, 8193)[0], 300),
+    ("n32767_ragged_last_bucket", lambda: scenes.scannet_like_batch(5, 2, 32767)[0], 400),
+    ("dups_20000", lambda: scenes.with_duplicates(scenes.uniform_cube(2, 20000, seed=21), 0.5), 900),
+    ("all_same_point_10000", lambda: np.full((1, 10000, 3), 0.25, np.float32), 20),
+    ("m_gt_distinct", lambda: np.repeat(scenes.uniform_cube(1, 40, seed=22), 300, axis=1), 100),
+    ("randn_negative_coords", lambda: np.random.RandomState(23).randn(2, 12345, 3).astype(np.float32), 500),
+    ("flat_cloud_z0", lambda: scenes.uniform_cube(2, 9999, seed=24) * np.array([1, 1, 0], np.float32), 333),
+    ("line_cloud", lambda: scenes.uniform_cube(1, 15000, seed=25) * np.array([1, 0, 0], np.float32) + np.float32(3.0), 200),
+    ("far_from_origin", lambda: scenes.scannet_like_batch(6, 1, 30000)[0] + np.float32(1000.0), 600),
+    ("b20_clouds", lambda: scenes.uniform_cube(20, 8500, seed=26), 64),
+]
+
+
+@pytest.mark.parametrize("name,make,m", FPS_BUCKET_CASES, ids=[c[0] for c in FPS_BUCKET_CASES])
+def test_fps_bucket_pruned_kernel_bit_exact(cuda, oracle, name, make, m):
+    """8193 .. 32768 points: the bucket-pruned single-CTA kernel (csrc/fps_bucket.cu) against the oracle, the reference's own kernel
+    and this library's full-scan cluster kernel -- duplicates, degenerate boxes, coordinates of either sign, ragged last bucket."""
+    xyz = make()
+    x = T(xyz, cuda)
+    L = _lib.lib()
+    scan = N(gspn_b200.farthest_point_sample(m, x))  # default: the full-scan cluster kernel
+    L.gspn_fps_tune(1)                               # opt in to the bucket-pruned kernel
+    try:
+        assert L.gspn_farthest_point_sample_workspace_bytes(xyz.shape[0], xyz.shape[1], m) > 0  # the bucket path is the one taken
+        got = N(gspn_b200.farthest_point_sample(m, x))
+    finally:
+        L.gspn_fps_tune(0)
+    assert np.array_equal(got, oracle.farthest_point_sample(m, xyz))
+    if refgpu.available():
+        assert np.array_equal(got, N(refgpu.fps(m, x)))
+    assert np.array_equal(got, scan)
+
+
 @pytest.mark.parametrize("n,m", [(131072 + 1000, 40), (300000, 64), (524288 + 7, 24)])
 def test_fps_data_prep_sized_clouds(cuda, oracle, n, m):
     """Above the register-resident limit: 16-CTA cluster streaming kernel (<= 524288 points), then the single-CTA fallback."""

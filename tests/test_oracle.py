@@ -196,3 +196,18 @@ def test_box_shrink_restatement(oracle):
             np.testing.assert_allclose(out[b, s, :3], (inside.max(0) + inside.min(0)) / 2, rtol=1e-6)
             np.testing.assert_allclose(out[b, s, 3:], inside.max(0) - inside.min(0) + 1e-3, rtol=1e-5)
 
+
+
+def test_blas_mlp_layer_of_the_reference_arm_matches_the_checker(oracle):
+    """bench.py's reference arm runs the shared MLP through a BLAS-class GEMM (TensorFlow-CPU stand-in); same layer, same numbers
+    up to summation order."""
+    rng = np.random.RandomState(5)
+    x = rng.randn(3, 50, 8, 67).astype(np.float32)
+    layer = {"weights": (rng.randn(67, 96) * 0.2).astype(np.float32), "biases": rng.randn(96).astype(np.float32) * 0.1,
+             "gamma": (0.75 + 0.5 * rng.rand(96)).astype(np.float32), "beta": rng.randn(96).astype(np.float32) * 0.1,
+             "moving_mean": rng.randn(96).astype(np.float32) * 0.1, "moving_variance": (0.75 + 0.5 * rng.rand(96)).astype(np.float32)}
+    a, b = oracle.mlp_layer(x, layer), oracle.mlp_layer_blas(x, layer)
+    assert a.shape == b.shape == (3, 50, 8, 96)
+    np.testing.assert_allclose(b, a, rtol=1e-4, atol=1e-5)
+    nobn = {"weights": layer["weights"], "biases": layer["biases"]}
+    np.testing.assert_allclose(oracle.mlp_layer_blas(x, nobn, relu=False), oracle.mlp_layer(x, nobn, relu=False), rtol=1e-4, atol=1e-5)
