@@ -63,6 +63,8 @@ SIGNATURES = {
     "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),
     "gspn_maxpool_argmax_f32": (c_int, [c_long, c_int, c_int, P, P, P, P]),
     "gspn_bn_act_pool_bwd_f32": (c_int, [c_long, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "gspn_bn_bwd_sums_f32": (c_int, [c_long, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P]),
+    "gspn_bn_bwd_apply_f32": (c_int, [c_long, c_long, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P]),
     "gspn_mlp_wgrad_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, P]),
     "gspn_group_rows_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_int, P]),

@@ -89,10 +89,10 @@ __global__ void __launch_bounds__(256) maxpool_argmax_kernel(long groups, int k,
 }
 
 // ---- dz = gamma*invstd * (dy' - s1/N - xhat*s2/N)      (batch-norm backward through the batch moments)
-__global__ void __launch_bounds__(256) bn_bwd_kernel(long rows, int c, BwdArgs a, const double *__restrict__ s1, const double *__restrict__ s2,
-                                                     float *__restrict__ dz) {
+__global__ void __launch_bounds__(256) bn_bwd_kernel(long rows, long norm_rows, int c, BwdArgs a, const double *__restrict__ s1,
+                                                     const double *__restrict__ s2, float *__restrict__ dz) {
     const long total = rows * c;
-    const float invn = 1.0f / (float)rows;
+    const float invn = 1.0f / (float)norm_rows;  // rows of the WHOLE batch the moments were taken over (all ranks under SyncBN)
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         long r = e / c;
         int col = (int)(e - r * c);
@@ -195,7 +195,36 @@ extern "C" int gspn_bn_act_pool_bwd_f32(long rows, int c, int pool, int relu, in
     dim3 grid((unsigned)ceil_div_l(rows, 256), ceil_div(c, 64)), block(64, 4);
     // bn == 0 (bn=False call sites): mean=0, invstd=gamma=1, beta=bias-free identity; the sums stay zero so dz = dy'
     if (bn) col_sums_kernel<1><<<grid, block, 0, s>>>(rows, c, z, a, s1, s2);
-    bn_bwd_kernel<<<ew_blocks(rows * c), 256, 0, s>>>(rows, c, a, s1, s2, dz);
+    bn_bwd_kernel<<<ew_blocks(rows * c), 256, 0, s>>>(rows, rows, c, a, s1, s2, dz);
+    return check_launch();
+}
+
+// The same backward in two calls, for batch norm over the WHOLE batch of a data-parallel job (SyncBN): the caller all-reduces
+// s1 / s2 between them and passes the global row count.
+extern "C" int gspn_bn_bwd_sums_f32(long rows, int c, int pool, int relu, const float *z, const float *dy, const int *argmax, const float *mean,
+                                    const float *invstd, const float *gamma, const float *beta, double *s1, double *s2, gspn_stream_t stream) {
+    GSPN_REQUIRE(rows > 0 && c > 0 && pool >= 1 && rows % pool == 0);
+    GSPN_REQUIRE_PTR(z); GSPN_REQUIRE_PTR(dy); GSPN_REQUIRE_PTR(mean); GSPN_REQUIRE_PTR(invstd); GSPN_REQUIRE_PTR(gamma); GSPN_REQUIRE_PTR(beta);
+    GSPN_REQUIRE_PTR(s1); GSPN_REQUIRE_PTR(s2);
+    if (pool > 1) GSPN_REQUIRE_PTR(argmax);
+    cudaStream_t s = as_stream(stream);
+    GSPN_CUDA_OK(cudaMemsetAsync(s1, 0, sizeof(double) * c, s));
+    GSPN_CUDA_OK(cudaMemsetAsync(s2, 0, sizeof(double) * c, s));
+    BwdArgs a = {z, dy, argmax, mean, invstd, gamma, beta, pool, relu};
+    dim3 grid((unsigned)ceil_div_l(rows, 256), ceil_div(c, 64)), block(64, 4);
+    col_sums_kernel<1><<<grid, block, 0, s>>>(rows, c, z, a, s1, s2);
+    return check_launch();
+}
+
+extern "C" int gspn_bn_bwd_apply_f32(long rows, long total_rows, int c, int pool, int relu, const float *z, const float *dy, const int *argmax,
+                                     const float *mean, const float *invstd, const float *gamma, const float *beta, const double *s1,
+                                     const double *s2, float *dz, gspn_stream_t stream) {
+    GSPN_REQUIRE(rows > 0 && total_rows >= rows && c > 0 && pool >= 1 && rows % pool == 0);
+    GSPN_REQUIRE_PTR(z); GSPN_REQUIRE_PTR(dy); GSPN_REQUIRE_PTR(mean); GSPN_REQUIRE_PTR(invstd); GSPN_REQUIRE_PTR(gamma); GSPN_REQUIRE_PTR(beta);
+    GSPN_REQUIRE_PTR(s1); GSPN_REQUIRE_PTR(s2); GSPN_REQUIRE_PTR(dz);
+    if (pool > 1) GSPN_REQUIRE_PTR(argmax);
+    BwdArgs a = {z, dy, argmax, mean, invstd, gamma, beta, pool, relu};
+    bn_bwd_kernel<<<ew_blocks(rows * c), 256, 0, as_stream(stream)>>>(rows, total_rows, c, a, s1, s2, dz);
     return check_launch();
 }
 

@@ -7,6 +7,12 @@ decay=bn_decay or 0.9, updates_collections=None, epsilon default 1e-3) -> relu (
 moments over every axis but channels; moving averages updated in place every step.
 Gradients flow to the layer variables and to `points` (features), as in the reference's registered gradients
 (GroupPointGrad, ThreeInterpolateGrad, GatherPointGrad); xyz, FPS, ball-query and three_nn indices carry none.
+
+Data parallel: the reference normalises over the WHOLE batch on its single GPU.  When torch.distributed is initialised
+with more than one rank and SYNC_BN is on (default), every batch-norm layer all-reduces [sum z, sum z^2, rows] in the forward and
+[sum dy', sum dy' xhat] in the backward (2C+1 / 2C doubles), so a batch sharded over W ranks gives the same activations, moving
+averages and -- after allreduce_gradients -- the same parameter gradients as the whole batch on one GPU
+(tests/test_syncbn.py).  SYNC_BN = False is per-replica batch norm.
 """
 import torch
 
@@ -14,6 +20,25 @@ from . import _lib, ops
 from ._lib import check
 
 BN_EPS = 1e-3
+SYNC_BN = True      # whole-batch statistics across ranks (only acts when torch.distributed has > 1 rank)
+SYNC_GROUP = None   # process group of the data-parallel replicas (None = the default group)
+
+
+def _world():
+    import torch.distributed as dist
+    return dist.get_world_size(SYNC_GROUP) if (SYNC_BN and dist.is_available() and dist.is_initialized()) else 1
+
+
+def allreduce_moments(s1, s2, rows):
+    """[sum, sum of squares, rows] of this rank's shard -> the same over every rank's shard (one all-reduce of 2C+1 doubles).
+    Works on CUDA (NCCL / gloo) and CPU (gloo) tensors; returns (s1, s2, total_rows)."""
+    import torch.distributed as dist
+    if _world() == 1:
+        return s1, s2, rows
+    buf = torch.cat([s1.double(), s2.double(), torch.tensor([float(rows)], dtype=torch.float64, device=s1.device)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=SYNC_GROUP)
+    c = s1.numel()
+    return buf[:c], buf[c:2 * c], int(round(float(buf[2 * c])))
 
 
 def _s():
@@ -49,14 +74,16 @@ class MlpLayerTrain(torch.autograd.Function):
             s1 = torch.empty(cout, dtype=torch.float64, device=dev)
             s2 = torch.empty(cout, dtype=torch.float64, device=dev)
             check(L.gspn_col_moments_f32(rows, cout, z.data_ptr(), s1.data_ptr(), s2.data_ptr(), _s()), "col_moments")
-            mean64 = s1 / rows
-            var64 = (s2 / rows - mean64 * mean64).clamp_(min=0.0)  # biased variance normalises (tf.nn.moments)
+            s1, s2, total_rows = allreduce_moments(s1, s2, rows)  # whole-batch moments across ranks (SyncBN); no-op on one rank
+            mean64 = s1 / total_rows
+            var64 = (s2 / total_rows - mean64 * mean64).clamp_(min=0.0)  # biased variance normalises (tf.nn.moments)
             mean, invstd = mean64.float(), torch.rsqrt(var64.float() + BN_EPS)
             with torch.no_grad():  # moving averages, updates_collections=None: updated as part of the forward
                 moving_mean.mul_(decay).add_(mean * (1.0 - decay))
                 moving_var.mul_(decay).add_(var64.float() * (1.0 - decay))
             g, be = gamma.contiguous(), beta.contiguous()
         else:
+            total_rows = rows
             mean = torch.zeros(cout, device=dev)
             invstd = torch.ones(cout, device=dev)
             g, be = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
@@ -71,14 +98,14 @@ class MlpLayerTrain(torch.autograd.Function):
             argmax = torch.empty((groups, cout), dtype=torch.int32, device=dev)
             check(L.gspn_maxpool_argmax_f32(groups, pool, cout, y.data_ptr(), out.data_ptr(), argmax.data_ptr(), _s()), "maxpool_argmax")
         ctx.save_for_backward(x, w, z, mean, invstd, g, be, argmax)
-        ctx.meta = (pool, int(relu), bn)
+        ctx.meta = (pool, int(relu), bn, total_rows)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
         x, w, z, mean, invstd, g, be, argmax = ctx.saved_tensors
-        pool, relu, bn = ctx.meta
+        pool, relu, bn, total_rows = ctx.meta
         rows, cin = x.shape
         cout = w.shape[1]
         dev = x.device
@@ -86,9 +113,19 @@ class MlpLayerTrain(torch.autograd.Function):
         s1 = torch.empty(cout, dtype=torch.float64, device=dev)
         s2 = torch.empty(cout, dtype=torch.float64, device=dev)
         dz = torch.empty((rows, cout), dtype=torch.float32, device=dev)
-        check(L.gspn_bn_act_pool_bwd_f32(rows, cout, pool, relu, int(bn), z.data_ptr(), dout.data_ptr(), None if argmax is None else argmax.data_ptr(),
-                                         mean.data_ptr(), invstd.data_ptr(), g.data_ptr(), be.data_ptr(), s1.data_ptr(), s2.data_ptr(),
-                                         dz.data_ptr(), None, None, _s()), "bn_act_pool_bwd")
+        am = None if argmax is None else argmax.data_ptr()
+        if bn and total_rows != rows:
+            # SyncBN: dz needs the sums over the whole batch; dgamma / dbeta below stay this rank's share (the gradient all-reduce adds them up)
+            check(L.gspn_bn_bwd_sums_f32(rows, cout, pool, relu, z.data_ptr(), dout.data_ptr(), am, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(),
+                                         be.data_ptr(), s1.data_ptr(), s2.data_ptr(), _s()), "bn_bwd_sums")
+            g1, g2, _ = allreduce_moments(s1, s2, rows)
+            g1, g2 = g1.contiguous(), g2.contiguous()
+            check(L.gspn_bn_bwd_apply_f32(rows, total_rows, cout, pool, relu, z.data_ptr(), dout.data_ptr(), am, mean.data_ptr(), invstd.data_ptr(),
+                                          g.data_ptr(), be.data_ptr(), g1.data_ptr(), g2.data_ptr(), dz.data_ptr(), _s()), "bn_bwd_apply")
+        else:
+            check(L.gspn_bn_act_pool_bwd_f32(rows, cout, pool, relu, int(bn), z.data_ptr(), dout.data_ptr(), am, mean.data_ptr(), invstd.data_ptr(),
+                                             g.data_ptr(), be.data_ptr(), s1.data_ptr(), s2.data_ptr(), dz.data_ptr(), None, None, _s()),
+                  "bn_act_pool_bwd")
         dW = torch.empty((cin, cout), dtype=torch.float32, device=dev)
         db = torch.empty(cout, dtype=torch.float32, device=dev)
         check(L.gspn_mlp_wgrad_f32(rows, cin, cout, x.data_ptr(), x.stride(0), dz.data_ptr(), dW.data_ptr(), db.data_ptr(), _s()), "mlp_wgrad")
@@ -176,13 +213,16 @@ def allreduce_gradients(params, group=None):
     """Data-parallel step: ONE bucketed all-reduce (mean) of every parameter gradient per step.
     Works with any initialised torch.distributed backend (NCCL on the GPUs, gloo in the CPU test)."""
     import torch.distributed as dist
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    if not params or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    # every rank contributes EVERY parameter (zeros where its shard produced no gradient), so the bucket has the same size everywhere
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat /= dist.get_world_size(group)
     o = 0
-    for g in grads:
-        g.copy_(flat[o:o + g.numel()].reshape(g.shape))
-        o += g.numel()
+    for p in params:
+        p.grad.copy_(flat[o:o + p.numel()].reshape(p.shape))
+        o += p.numel()

@@ -245,6 +245,14 @@ int gspn_maxpool_argmax_f32(long groups, int k, int c, const float *y, float *ou
 int gspn_bn_act_pool_bwd_f32(long rows, int c, int pool, int relu, int bn, const float *z, const float *dy, const int *argmax,
                              const float *mean, const float *invstd, const float *gamma, const float *beta,
                              double *s1, double *s2, float *dz, float *dgamma, float *dbeta, gspn_stream_t stream);
+/* The same backward split in two, for batch norm over the WHOLE batch of a data-parallel job (utils/tf_util.py:530-534 normalises
+ * over every row of the batch; sharded over ranks that needs the sums all-reduced): _sums writes this rank's s1 / s2, the caller
+ * all-reduces them (and the row count), _apply computes dz with the global sums and total_rows. */
+int gspn_bn_bwd_sums_f32(long rows, int c, int pool, int relu, const float *z, const float *dy, const int *argmax, const float *mean,
+                         const float *invstd, const float *gamma, const float *beta, double *s1, double *s2, gspn_stream_t stream);
+int gspn_bn_bwd_apply_f32(long rows, long total_rows, int c, int pool, int relu, const float *z, const float *dy, const int *argmax,
+                          const float *mean, const float *invstd, const float *gamma, const float *beta, const double *s1,
+                          const double *s2, float *dz, gspn_stream_t stream);
 /* dW (cin,cout) = x^T dz, dbias (cout, may be NULL) = colsum(dz); both zeroed here; x has row stride ldx. */
 int gspn_mlp_wgrad_f32(long rows, int cin, int cout, const float *x, int ldx, const float *dz, float *dW, float *dbias,
                        gspn_stream_t stream);

@@ -1,50 +1,81 @@
-"""BASELINE config 3: GSPN shape-proposal context encoder (multi_encoding_net, models/model_rpointnet.py:377): 128 seeds per
-scene, radii 0.5/1.0/1.5, nsample 256/256/512, mlp [64,128,256] per radius, batch 16 scenes of 18000 points (config.py:14).
-Reports ms, seeds/s, scene/s and the tensor-pipe rate of the grouped MLP. Run under gpurun."""
+"""BASELINE config 3: GSPN shape-proposal context encoder (multi_encoding_net, models/model_rpointnet.py:28-77, call :377): 128
+seeds per scene, radii 0.5/1.0/1.5, nsample 256/256/512, mlp [64,128,256] per radius, GLOBAL batch 16 scenes of 18000 points
+(models/config.py:14), batch-sharded over the ranks (strong scaling: every rank owns 16 / world scenes, no collective).
+
+  python bench.py --workload cfg3 [--steps K --warmup W --precision bf16x3|bf16|fp32]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --workload cfg3 --gpus N
+
+One step = FPS of the seeds' cloud is NOT included (the model passes fps_idx in, :377); it is the three ball queries + grouping +
+grouped MLP + max-pool.  Prints one JSON line (rank 0): scenes/s over the whole job, CUDA-event timed, max over ranks."""
+import argparse
 import json
 import os
 import sys
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gspn_b200
 from gspn_b200 import context_encoder, scenes
 from gspn_b200 import pointnet_util as pu
 
-dev = torch.device("cuda:0")
-B, N, SEEDS = 16, 18000, 128
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=5)
+ap.add_argument("--precision", default=None)
+ap.add_argument("--gpus", type=int, default=1)
+args = ap.parse_args()
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+B_GLOBAL, N, SEEDS = 16, 18000, 128
+lo, hi = scenes.shard_scenes(B_GLOBAL, rank, world)
+B = hi - lo
 radii, ks, mlps = [0.5, 1.0, 1.5], [256, 256, 512], [[64, 128, 256]] * 3
-xyz, col = scenes.scannet_like_batch(0, B, N)
-x, c = torch.from_numpy(xyz).to(dev), torch.from_numpy(col).to(dev)
+prec = args.precision or pu.DEFAULT_PRECISION
+ROT = 4  # distinct scene sets cycled through the steps
+inputs = []
+for rset in range(ROT):
+    xyz, col = scenes.scannet_like_batch(rset * B_GLOBAL + lo, B, N)
+    x, c = torch.from_numpy(xyz).to(dev), torch.from_numpy(col).to(dev)
+    inputs.append((x, c, gspn_b200.farthest_point_sample(SEEDS, x), torch.zeros((B, SEEDS, 3), device=dev)))
 store = pu.VariableStore(device=dev, seed=7)
-fps = gspn_b200.farthest_point_sample(SEEDS, x)
-shift = torch.zeros((B, SEEDS, 3), device=dev)
 
 
-def run(prec):
+def run(i):
+    x, c, fps, shift = inputs[i % ROT]
     return context_encoder.multi_encoding_net(x, c, SEEDS, radii, ks, mlps, [], False, None, "ctx", use_xyz=True, shift_pred=shift, fps_idx=fps,
                                               variables=store, precision=prec)[1]
 
 
-res = {}
-for prec in ("bf16", "fp32"):
-    for _ in range(3):
-        out = run(prec)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(10):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); out = run(prec); b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
-    ms = float(np.median(ts))
-    flops = 2.0 * B * SEEDS * sum(ks) * (6 * 64 + 64 * 128 + 128 * 256)
-    res[prec] = dict(ms=ms, scenes_per_s=B / ms * 1e3, seeds_per_s=B * SEEDS / ms * 1e3, mlp_gflop=flops / 1e9, tflops_if_all_mlp=flops / ms / 1e9)
-    print(prec, res[prec], tuple(out.shape), flush=True)
-a = run("bf16"); b = run("fp32")
-res["bf16_vs_fp32_relerr"] = float((a - b).abs().max() / b.abs().max())
-print("bf16 vs fp32 normwise", res["bf16_vs_fp32_relerr"])
-os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/cfg3_context_encoder.json", "w"), indent=1)
+for w in range(max(3, args.warmup)):
+    out = run(w)
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for s in range(args.steps):
+    out = run(s)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / args.steps
+if world > 1:
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+if rank == 0:
+    flops = 2.0 * B_GLOBAL * SEEDS * sum(ks) * (6 * 64 + 64 * 128 + 128 * 256)
+    print(json.dumps({
+        "metric": "GSPN context encoder (multi_encoding_net) scenes/sec, 16 scenes x 18000 pts x 128 seeds", "value": B_GLOBAL / (ms * 1e-3),
+        "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+        "config": {"workload": "config3: multi_encoding_net forward, radii 0.5/1.0/1.5, nsample 256/256/512, mlp [64,128,256] x3, global batch 16 "
+                               "scenes sharded over the ranks", "scenes_per_rank": B, "seeds_per_scene": SEEDS},
+        "mlp_gflop": flops / 1e9, "algorithmic_tflops": flops / (ms * 1e-3) / 1e12, "out_shape": list(out.shape)}))
+if world > 1:
+    dist.destroy_process_group()
