@@ -25,6 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout and would precede the JSON line
 
 NPOINTS = 32768
 SCENES_PER_GPU = 8
@@ -323,6 +325,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the labelled extras (bf16 line, fp32-download e2e, reference-GPU column)")
     ap.add_argument("--depth", type=int, default=8, help="batches kept in flight (CUDA-graph lanes on separate streams)")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--fps-mapping", default=None, help="A/B door: threads,ppt,cluster of the FPS kernel for 32768-point clouds")
+    ap.add_argument("--fps-buckets", action="store_true", help="A/B door: the bucket-pruned single-CTA FPS kernel")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 = BASELINE.json's headline (default); cfg3 / cfg4 = tools/bench_cfg3.py / tools/bench_cfg4.py under the same launch")
     args = ap.parse_args()
@@ -343,6 +347,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gspn_b200 has no CPU path (use --impl reference for the CPU arm)")
     L = _lib.lib()  # fail loudly if the extension is missing
+    if args.fps_mapping:
+        L.gspn_fps_tune_mapping(*[int(v) for v in args.fps_mapping.split(",")])
+    if args.fps_buckets:
+        L.gspn_fps_tune(1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -34,6 +34,7 @@ SIGNATURES = {
     "gspn_farthest_point_sample": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "gspn_farthest_point_sample_cfg": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P]),
     "gspn_fps_tune": (None, [c_int]),
+    "gspn_fps_tune_mapping": (None, [c_int, c_int, c_int]),
     "gspn_fps_bucket_profile": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P, P]),
     "gspn_fps_profile": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P]),
     "gspn_gather_point": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),

@@ -503,6 +503,7 @@ int gspn_fps_bucket_launch(int b, int n, int m, const float *inp, int *out, void
 // Opt-in (gspn_fps_tune(1)): exact and 80x fewer distance evaluations, but measured SLOWER per cloud than the full-scan cluster kernel
 // (2.4 ms vs 1.04 ms at 32768 -> 2048): off by default.
 static int g_fps_buckets = 0;
+static int g_fps_big[3] = {0, 0, 0};  // tuning door (gspn_fps_tune_mapping): (threads, ppt, cluster) for clouds above 16384 points
 
 // Tuning door: per-phase cycle counts of thread 0 (compute+tournament, warp reduce, exchange, table reduce),
 // summed over the m-1 rounds, for the (threads, ppt, cluster) shapes the default table uses.
@@ -534,6 +535,7 @@ extern "C" size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m
 }
 
 extern "C" void gspn_fps_tune(int use_buckets) { g_fps_buckets = use_buckets != 0; }
+extern "C" void gspn_fps_tune_mapping(int threads, int ppt, int cluster) { g_fps_big[0] = threads; g_fps_big[1] = ppt; g_fps_big[2] = cluster; }
 
 extern "C" int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
                                        long long *prof3, gspn_stream_t stream) {
@@ -552,6 +554,7 @@ extern "C" int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *
     GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out);
     int t0, p0, c0;
     choose_cfg(n, &t0, &p0, &c0);
+    if (n > 16384 && g_fps_big[0] > 0 && (long)g_fps_big[0] * g_fps_big[1] * g_fps_big[2] >= n) { t0 = g_fps_big[0]; p0 = g_fps_big[1]; c0 = g_fps_big[2]; }
     if (threads <= 0) threads = t0;
     if (ppt <= 0) ppt = p0;
     if (cluster <= 0) cluster = c0;

@@ -31,8 +31,15 @@
 
 namespace gspn {
 
-constexpr int kFbWarps = 12, kFbThreads = kFbWarps * 32, kFbSlots = 86;  // slots = buckets per warp (up to three per lane)
-constexpr int kFbBuckets = 1024;                                         // 12 x 86 = 1032 slots, the last 8 stay empty
+#ifndef GSPN_FB_WARPS
+#define GSPN_FB_WARPS 16
+#endif
+// 16 warps x 64 slots (128 registers per thread) or 12 warps x 86 slots (170 registers): 32768 of the SM's 65536 registers hold
+// distances either way; what is left per thread decides whether the round loop compiles without local-memory spills, which with
+// 220 KB of shared memory carved out have no L1 to land in.
+constexpr int kFbWarps = GSPN_FB_WARPS, kFbThreads = kFbWarps * 32, kFbSlots = (1024 + kFbWarps - 1) / kFbWarps;  // slots = buckets per warp
+constexpr int kFbQuadWarps = kFbWarps / 4;                               // warps sharing a TMEM lane quadrant
+constexpr int kFbBuckets = 1024;                                         // 12 x 86 = 1032 slots: the last 8 stay empty
 constexpr int kFbMaxPoints = kFbBuckets * 32;                            // 32768
 constexpr int kFbSlotsAll = kFbWarps * kFbSlots;                         // 1032
 constexpr int kFbCells = 32 * 32 * 32;
@@ -171,7 +178,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
     }
     __syncthreads();  // the sort is complete and visible to the CTA; cellcnt is dead: X may be written
     // ---- P5: resident copy.  Thread (warp, lane) owns point `lane` of the bucket in each of its warp's slots.
-    // TMEM column of slot r: 3 r + (warp / 4) for y, + 256 for z -- three warps share a lane quadrant (256 columns per array).
+    // TMEM column of slot r: kFbQuadWarps * r + (warp / 4) for y, + 256 for z -- the warps sharing a lane quadrant interleave
+    // their slots (256 columns per array).
     const uint32_t tY = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2);
     float d[kFbSlots];
 #pragma unroll
@@ -184,8 +192,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
         if (j < kFbBuckets) {
             X[pos] = v.x;
             IDX[pos] = (unsigned short)__float_as_int(v.w);
-            fb_tst1(tY + 3 * r, __float_as_uint(v.y));
-            fb_tst1(tY + 256 + 3 * r, __float_as_uint(v.z));
+            fb_tst1(tY + kFbQuadWarps * r, __float_as_uint(v.y));
+            fb_tst1(tY + 256 + kFbQuadWarps * r, __float_as_uint(v.z));
         }
         d[r] = ok ? 1e38f : -1.0f;  // tf_sampling_g.cu:118; padding never wins (distances are >= 0)
         const int ilx = __reduce_min_sync(GSPN_FULL_MASK, ok ? fb_ord(v.x) : 0x7FFFFFFF), ihx = __reduce_max_sync(GSPN_FULL_MASK, ok ? fb_ord(v.x) : (int)0x80000000);
@@ -212,6 +220,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
         bmax2 = __float_as_int(nonempty(64 + lane) ? 1e38f : -1.0f);
         mykey[0] = 0xFFFFFFFFu; mykey[32] = 0xFFFFFFFFu;
         if (64 + lane < kFbSlots) mykey[64] = 0xFFFFFFFFu;
+        if (kFbSlots <= 64) bmax2 = __float_as_int(-1.0f);
     }
     // the warp's cached candidate (uniform across lanes): max distance bits, key, coordinates
     if (lane == 0) {
@@ -224,22 +233,28 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
     if (tid == 0) o[0] = 0;
     unsigned acc_touched = 0, acc_full = 0, t_start = 0, ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;  // PROF only
     if (PROF) t_start = (unsigned)clock();
-    const bool own2 = 64 + lane < kFbSlots;
+    const bool own2 = kFbSlots > 64 && 64 + lane < kFbSlots;
 
     for (int r = 1; r < m; ++r) {
         const int par = r & 1;
         if (PROF) c0 = (unsigned)clock();
         {
+            // one box at a time (the empty asm keeps the compiler from hoisting all 18 loads: registers are what this kernel is short of)
             const bool t0 = fb_box_bound(mybox[0], mybox[kFbSlotsAll], mybox[2 * kFbSlotsAll], mybox[3 * kFbSlotsAll], mybox[4 * kFbSlotsAll],
                                          mybox[5 * kFbSlotsAll], sx, sy, sz) < __int_as_float(bmax0);
+            asm volatile("" ::: "memory");
             const bool t1 = fb_box_bound(mybox[32], mybox[kFbSlotsAll + 32], mybox[2 * kFbSlotsAll + 32], mybox[3 * kFbSlotsAll + 32],
                                          mybox[4 * kFbSlotsAll + 32], mybox[5 * kFbSlotsAll + 32], sx, sy, sz) < __int_as_float(bmax1);
             bool t2 = false;
-            if (own2)
-                t2 = fb_box_bound(mybox[64], mybox[kFbSlotsAll + 64], mybox[2 * kFbSlotsAll + 64], mybox[3 * kFbSlotsAll + 64],
-                                  mybox[4 * kFbSlotsAll + 64], mybox[5 * kFbSlotsAll + 64], sx, sy, sz) < __int_as_float(bmax2);
+            if constexpr (kFbSlots > 64) {
+                asm volatile("" ::: "memory");
+                if (own2)
+                    t2 = fb_box_bound(mybox[64], mybox[kFbSlotsAll + 64], mybox[2 * kFbSlotsAll + 64], mybox[3 * kFbSlotsAll + 64],
+                                      mybox[4 * kFbSlotsAll + 64], mybox[5 * kFbSlotsAll + 64], sx, sy, sz) < __int_as_float(bmax2);
+            }
             // NOT an array: a runtime-indexed mask[S] lives in local memory, and with 220 KB of shared memory no L1 is left to catch it
-            const unsigned mask0 = __ballot_sync(GSPN_FULL_MASK, t0), mask1 = __ballot_sync(GSPN_FULL_MASK, t1), mask2 = __ballot_sync(GSPN_FULL_MASK, t2);
+            const unsigned mask0 = __ballot_sync(GSPN_FULL_MASK, t0), mask1 = __ballot_sync(GSPN_FULL_MASK, t1),
+                           mask2 = kFbSlots > 64 ? __ballot_sync(GSPN_FULL_MASK, t2) : 0u;
             if (PROF) { acc_touched += __popc(mask0) + __popc(mask1) + __popc(mask2); c1 = (unsigned)clock(); c2 = c1; }
             if (mask0 | mask1 | mask2) {
                 bool dirty = false;
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
                 // picks (R is warp-uniform).  Unrolling the body per slot instead costs 100 KB of code and an instruction-cache
                 // miss chain per touched bucket.
 #pragma unroll 1
-                for (int S = 0; S < 3; ++S) {
+                for (int S = 0; S < (kFbSlots > 64 ? 3 : 2); ++S) {
                     unsigned mk = S == 0 ? mask0 : (S == 1 ? mask1 : mask2);
 #pragma unroll 1
                     while (mk) {
@@ -256,8 +271,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
                         mk &= mk - 1;
                         const int R = 32 * S + L;
                         uint32_t yb, zb;
-                        fb_tld1(tY + 3 * R, yb);
-                        fb_tld1(tY + 256 + 3 * R, zb);
+                        fb_tld1(tY + kFbQuadWarps * R, yb);
+                        fb_tld1(tY + 256 + kFbQuadWarps * R, zb);
                         const int pos = (R * kFbWarps + warp) * 32 + lane;
                         const float x = X[pos];
                         const int oi = IDX[pos];
@@ -267,8 +282,10 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
                         switch (R) {
 #define FB_CASE(i) case i: dold = d[i]; dd = fminf(dn, dold); d[i] = dd; break;
 #define FB_CASE8(i) FB_CASE(i) FB_CASE(i + 1) FB_CASE(i + 2) FB_CASE(i + 3) FB_CASE(i + 4) FB_CASE(i + 5) FB_CASE(i + 6) FB_CASE(i + 7)
-                            FB_CASE8(0) FB_CASE8(8) FB_CASE8(16) FB_CASE8(24) FB_CASE8(32) FB_CASE8(40) FB_CASE8(48) FB_CASE8(56) FB_CASE8(64) FB_CASE8(72)
-                            FB_CASE(80) FB_CASE(81) FB_CASE(82) FB_CASE(83) FB_CASE(84) FB_CASE(85)
+                            FB_CASE8(0) FB_CASE8(8) FB_CASE8(16) FB_CASE8(24) FB_CASE8(32) FB_CASE8(40) FB_CASE8(48) FB_CASE8(56)
+#if GSPN_FB_WARPS == 12
+                            FB_CASE8(64) FB_CASE8(72) FB_CASE(80) FB_CASE(81) FB_CASE(82) FB_CASE(83) FB_CASE(84) FB_CASE(85)
+#endif
 #undef FB_CASE8
 #undef FB_CASE
                             default: dd = dold = dn; break;
@@ -316,8 +333,8 @@ __global__ void __launch_bounds__(kFbThreads, 1) fps_bucket_kernel(int n, int m,
                     const unsigned iw = rs < 32 ? iswin0 : (rs < 64 ? iswin1 : iswin2);
                     const int ls = __ffs(__ballot_sync(GSPN_FULL_MASK, (iw >> (rs & 31)) & 1u)) - 1;
                     uint32_t yb, zb;
-                    fb_tld1(tY + 3 * rs, yb);
-                    fb_tld1(tY + 256 + 3 * rs, zb);
+                    fb_tld1(tY + kFbQuadWarps * rs, yb);
+                    fb_tld1(tY + 256 + kFbQuadWarps * rs, zb);
                     const float wx = X[(rs * kFbWarps + warp) * 32 + ls];
                     fb_twait_ld();
                     if (lane == ls) {

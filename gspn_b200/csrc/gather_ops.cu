@@ -78,6 +78,61 @@ __global__ void __launch_bounds__(kThreads) three_interpolate_v4_kernel(long tot
     }
 }
 
+// The streaming form: a group of G = c/8 lanes (8, 16 or 32) owns an output row; ONE lane of the group loads the row's three
+// indices and weights and the group shares them through shuffles (the v4 kernel re-loads all six values in every thread), every lane
+// moves 32 bytes per access (LDG.E.256 gathers, a streaming STG.E.256), and each group keeps two rows (six 256-bit gathers per lane)
+// in flight.  Rounding as the CPU op: (p1*w1 + p2*w2) + p3*w3 without FMA.
+struct __align__(32) F8 { float v[8]; };
+__device__ __forceinline__ F8 ldg_f8(const float *p) {
+    F8 r;
+    asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stcs_f8(float *p, const F8 &r) {
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]),
+                 "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
+                 : "memory");
+}
+template <int G>
+__global__ void __launch_bounds__(kThreads) three_interpolate_rows_kernel(long rows, int m, int n, const float *__restrict__ points,
+                                                                          const int *__restrict__ idx, const float *__restrict__ weight,
+                                                                          float *__restrict__ out, const FastDiv div_n) {
+    constexpr int C = G * 8;
+    constexpr int RPW = 32 / G;  // rows per warp-step
+    const int lane = threadIdx.x & 31, g = lane / G, l = lane % G;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long r0 = warp * (2 * RPW); r0 < rows; r0 += nwarps * (2 * RPW)) {
+        F8 a[2], b[2], c[2];
+        float w1[2], w2[2], w3[2];
+        long row[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            row[u] = r0 + u * RPW + g;
+            const bool ok = row[u] < rows;
+            const long rr = ok ? row[u] : 0;
+            int iv = 0;
+            float wv = 0.f;
+            if (l < 3) { iv = __ldg(idx + rr * 3 + l); wv = __ldg(weight + rr * 3 + l); }  // lanes 0..2 of the group: one value each
+            const int i1 = __shfl_sync(GSPN_FULL_MASK, iv, g * G), i2 = __shfl_sync(GSPN_FULL_MASK, iv, g * G + 1),
+                      i3 = __shfl_sync(GSPN_FULL_MASK, iv, g * G + 2);
+            w1[u] = __shfl_sync(GSPN_FULL_MASK, wv, g * G); w2[u] = __shfl_sync(GSPN_FULL_MASK, wv, g * G + 1);
+            w3[u] = __shfl_sync(GSPN_FULL_MASK, wv, g * G + 2);
+            const float *base = points + (size_t)div_n.div((uint32_t)rr) * m * C + l * 8;
+            a[u] = ldg_f8(base + (size_t)i1 * C); b[u] = ldg_f8(base + (size_t)i2 * C); c[u] = ldg_f8(base + (size_t)i3 * C);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (row[u] >= rows) continue;
+            F8 o;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o.v[k] = interp3(a[u].v[k], b[u].v[k], c[u].v[k], w1[u], w2[u], w3[u]);
+            stcs_f8(out + row[u] * C + l * 8, o);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) three_interpolate_kernel(long total, int m, int n, int c, const float *__restrict__ points,
                                                                      const int *__restrict__ idx, const float *__restrict__ weight,
                                                                      float *__restrict__ out) {
@@ -256,7 +311,20 @@ extern "C" int gspn_three_interpolate(int b, int m, int c, int n, const float *p
     GSPN_REQUIRE(b >= 0 && m > 0 && c > 0 && n >= 0);  // tf_interpolate.cpp:197-206
     if (b == 0 || n == 0) return GSPN_OK;
     GSPN_REQUIRE_PTR(points); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(weight); GSPN_REQUIRE_PTR(out);
-    if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
+    const long rows = (long)b * n;
+    const bool a32 = ((reinterpret_cast<uintptr_t>(points) | reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
+    if (a32 && rows < (1L << 31) && (c == 64 || c == 128 || c == 256)) {
+        // one group of c/8 lanes per row, two rows in flight per group; grid sized so that every SM holds 8 CTAs of work at most
+        const int rpw = 2 * (256 / c);  // rows per warp per iteration
+        long blk = ceil_div_l(ceil_div_l(rows, rpw) * 32, kThreads);
+        const long cap = 148L * 8 * 4;
+        if (blk > cap) blk = cap;
+        const FastDiv dn((uint32_t)n);
+        cudaStream_t st = as_stream(stream);
+        if (c == 64) three_interpolate_rows_kernel<8><<<(unsigned)blk, kThreads, 0, st>>>(rows, m, n, points, idx, weight, out, dn);
+        else if (c == 128) three_interpolate_rows_kernel<16><<<(unsigned)blk, kThreads, 0, st>>>(rows, m, n, points, idx, weight, out, dn);
+        else three_interpolate_rows_kernel<32><<<(unsigned)blk, kThreads, 0, st>>>(rows, m, n, points, idx, weight, out, dn);
+    } else if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
         long total = (long)b * n * (c / 4);
         three_interpolate_v4_kernel<<<blocks_for(total), kThreads, 0, as_stream(stream)>>>(total, m, n, c / 4, (const float4 *)points, idx, weight, (float4 *)out);
     } else {

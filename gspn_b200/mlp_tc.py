@@ -256,7 +256,7 @@ def fp_interp_mlp(points1, points2, idx, weight, layers, store, scope, timers, p
     L = _lib.lib()
     rows = b * n
     widths = [l["weights"].shape[1] for l in layers]
-    if FP_COMMUTE and len(layers) >= 2 and c1 <= 4 and widths[0] % 64 == 0 and widths[0] <= 256 and n >= 2 * m and (b * n) < 2 ** 31:
+    if FP_COMMUTE and len(layers) >= 2 and c1 <= 4 and widths[0] == 128 and n >= 2 * m and (b * n) < 2 ** 31:
         out, out_h = _fp_commuted(points1, points2, idx, weight, layers, precision, timers, scope, want_half, want_f32)
     else:
         ld = _pad64(c1 + c2)

@@ -22,6 +22,8 @@ from ._lib import check
 BN_EPS = 1e-3
 SYNC_BN = True      # whole-batch statistics across ranks (only acts when torch.distributed has > 1 rank)
 SYNC_GROUP = None   # process group of the data-parallel replicas (None = the default group)
+EQUAL_SHARDS = True # every rank feeds the same number of rows per layer (batch sharding of equal scenes): the global row count is
+                    # rows * world and needs no communication -- and no host synchronisation inside the step
 
 
 def _world():
@@ -29,16 +31,23 @@ def _world():
     return dist.get_world_size(SYNC_GROUP) if (SYNC_BN and dist.is_available() and dist.is_initialized()) else 1
 
 
-def allreduce_moments(s1, s2, rows):
-    """[sum, sum of squares, rows] of this rank's shard -> the same over every rank's shard (one all-reduce of 2C+1 doubles).
+def allreduce_moments(s1, s2, rows, buf=None):
+    """[sum, sum of squares, rows] of this rank's shard -> the same over every rank's shard: ONE all-reduce of 2C (+1) doubles.
+    buf: optional (2C,) tensor whose halves ARE s1 and s2 (then nothing is concatenated and the result aliases it).
     Works on CUDA (NCCL / gloo) and CPU (gloo) tensors; returns (s1, s2, total_rows)."""
     import torch.distributed as dist
-    if _world() == 1:
+    world = _world()
+    if world == 1:
         return s1, s2, rows
+    c = s1.numel()
+    if EQUAL_SHARDS:
+        if buf is None:
+            buf = torch.cat([s1.double(), s2.double()])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=SYNC_GROUP)
+        return buf[:c], buf[c:2 * c], rows * world
     buf = torch.cat([s1.double(), s2.double(), torch.tensor([float(rows)], dtype=torch.float64, device=s1.device)])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=SYNC_GROUP)
-    c = s1.numel()
-    return buf[:c], buf[c:2 * c], int(round(float(buf[2 * c])))
+    return buf[:c], buf[c:2 * c], int(round(float(buf[2 * c])))  # reads the count back: one host synchronisation per layer
 
 
 def _s():
@@ -71,10 +80,10 @@ class MlpLayerTrain(torch.autograd.Function):
         bn = gamma is not None
         z = _linear(x, w, bias.contiguous())
         if bn:
-            s1 = torch.empty(cout, dtype=torch.float64, device=dev)
-            s2 = torch.empty(cout, dtype=torch.float64, device=dev)
+            mom = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+            s1, s2 = mom[:cout], mom[cout:]
             check(L.gspn_col_moments_f32(rows, cout, z.data_ptr(), s1.data_ptr(), s2.data_ptr(), _s()), "col_moments")
-            s1, s2, total_rows = allreduce_moments(s1, s2, rows)  # whole-batch moments across ranks (SyncBN); no-op on one rank
+            s1, s2, total_rows = allreduce_moments(s1, s2, rows, mom)  # whole-batch moments across ranks (SyncBN); no-op on one rank
             mean64 = s1 / total_rows
             var64 = (s2 / total_rows - mean64 * mean64).clamp_(min=0.0)  # biased variance normalises (tf.nn.moments)
             mean, invstd = mean64.float(), torch.rsqrt(var64.float() + BN_EPS)
@@ -110,16 +119,16 @@ class MlpLayerTrain(torch.autograd.Function):
         cout = w.shape[1]
         dev = x.device
         dout = dout.contiguous()
-        s1 = torch.empty(cout, dtype=torch.float64, device=dev)
-        s2 = torch.empty(cout, dtype=torch.float64, device=dev)
+        mom = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+        s1, s2 = mom[:cout], mom[cout:]
         dz = torch.empty((rows, cout), dtype=torch.float32, device=dev)
         am = None if argmax is None else argmax.data_ptr()
         if bn and total_rows != rows:
             # SyncBN: dz needs the sums over the whole batch; dgamma / dbeta below stay this rank's share (the gradient all-reduce adds them up)
             check(L.gspn_bn_bwd_sums_f32(rows, cout, pool, relu, z.data_ptr(), dout.data_ptr(), am, mean.data_ptr(), invstd.data_ptr(), g.data_ptr(),
                                          be.data_ptr(), s1.data_ptr(), s2.data_ptr(), _s()), "bn_bwd_sums")
-            g1, g2, _ = allreduce_moments(s1, s2, rows)
-            g1, g2 = g1.contiguous(), g2.contiguous()
+            dbeta_local, dgamma_local = s1.float(), s2.float()  # this rank's share, before the sums become global
+            g1, g2, _ = allreduce_moments(s1, s2, rows, mom)
             check(L.gspn_bn_bwd_apply_f32(rows, total_rows, cout, pool, relu, z.data_ptr(), dout.data_ptr(), am, mean.data_ptr(), invstd.data_ptr(),
                                           g.data_ptr(), be.data_ptr(), g1.data_ptr(), g2.data_ptr(), dz.data_ptr(), _s()), "bn_bwd_apply")
         else:
@@ -132,8 +141,11 @@ class MlpLayerTrain(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _linear(dz, w.t().contiguous(), torch.zeros(cin, device=dev))
-        dgamma = s2.float() if bn else None
-        dbeta = s1.float() if bn else None
+        if bn and total_rows != rows:
+            dgamma, dbeta = dgamma_local, dbeta_local
+        else:
+            dgamma = s2.float() if bn else None
+            dbeta = s1.float() if bn else None
         return dx, dW, db, dgamma, dbeta, None, None, None, None, None
 
 

@@ -89,6 +89,9 @@ int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *o
  * prof3[1] = rounds, prof3[2] = bucket updates, prof3[3..7] = warp 0's cycles in: box tests, bucket updates, warp argmax, barrier
  * wait, table reduce, prof3[8] = bucket updates that needed the full argmax (prof3: 12 x int64, zeroed by the caller). */
 void gspn_fps_tune(int use_buckets);
+/* (threads per CTA, points per thread, CTAs per cluster) of the register-resident kernel for clouds above 16384 points; 0,0,0 = the
+ * built-in table.  Same results for every legal choice. */
+void gspn_fps_tune_mapping(int threads, int ppt, int cluster);
 int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
                             long long *prof3, gspn_stream_t stream);
 
@@ -223,7 +226,7 @@ int gspn_mlp_chain_gather(int b, int n, int m, int nsample, int c, const float *
  * shift 0 / no ReLU); the kernel's producer warps gather the three rows of y2 per point, finish layer 0 on the CUDA cores
  * (act(scale[0] * (w1*y2[i1] + w2*y2[i2] + w3*y2[i3] + points1 @ w0b) + shift[0])) and feed layers 1.. to the tensor cores.
  *   idx / weight (b,n,3) from gspn_three_nn; points1 (b,n,c1) with c1 <= 4, or NULL; w0b = W0[c2:] (c1,n0) f32
- *   nlayers >= 2 counts layer 0; dims[0] ignored, dims[1] = n0 (multiple of 64), dims[l+1] = cout of layer l; wimg[0] unused. */
+ *   nlayers >= 2 counts layer 0; dims[0] ignored, dims[1] = n0 = 128, dims[l+1] = cout of layer l; wimg[0] unused. */
 int gspn_mlp_chain_fp(int b, int n, int m, int c1, const float *y2, const int *idx, const float *weight, const float *points1,
                       const float *w0b, int nlayers, const int *dims, const void *const *wimg, const float *const *scale,
                       const float *const *shift, const int *relu, float *out_f32, void *out_h, int out_h_dtype, int arith,

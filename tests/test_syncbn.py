@@ -32,7 +32,9 @@ def _spawn(fn, world, *args, timeout=300):
     out = q.get(timeout=timeout)
     for p in procs:
         p.join(timeout=60)
-        assert p.exitcode == 0
+        if p.is_alive():
+            p.terminate()
+        assert p.exitcode == 0 or (isinstance(out, dict) and "error" in out)
     return out
 
 
@@ -40,6 +42,7 @@ def _moments_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from gspn_b200 import train
+    train.EQUAL_SHARDS = False  # unequal shards below: the row count has to travel
     g = torch.Generator().manual_seed(5)
     z = torch.randn(1000, 7, generator=g, dtype=torch.float64) * 3 + 1
     rows = [400, 600]  # unequal shards: the row count travels with the sums
@@ -80,6 +83,15 @@ def _layers(rng, cin, widths, dev):
 
 
 def _syncbn_worker(rank, world, port, q):
+    try:
+        _syncbn_body(rank, world, port, q)
+    except Exception as e:  # fail fast instead of leaving the parent on its queue
+        import traceback
+        q.put({"error": "rank %d: %s" % (rank, traceback.format_exc())})
+        raise
+
+
+def _syncbn_body(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from gspn_b200 import train
@@ -118,6 +130,7 @@ def _syncbn_worker(rank, world, port, q):
 
 @pytest.mark.gpu
 def test_sharded_batch_norm_equals_whole_batch(cuda):
-    res = _spawn(_syncbn_worker, 2)
+    res = _spawn(_syncbn_worker, 2, timeout=120)
+    assert "error" not in res, res["error"]
     for name, (got, exp) in res.items():
         np.testing.assert_allclose(got, exp, rtol=2e-3, atol=2e-5, err_msg=name)

@@ -55,14 +55,28 @@ def run(i):
 for w in range(max(3, args.warmup)):
     out = run(w)
 torch.cuda.synchronize()
+# one CUDA graph per input set: a step is ~25 kernel launches of 10-100 us, which Python cannot issue fast enough
+graphs, outs = [], []
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    for i in range(ROT):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+            outs.append(run(i))
+        graphs.append(g)
+torch.cuda.synchronize()
+for w in range(max(3, args.warmup)):
+    graphs[w % ROT].replay()
+torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for s in range(args.steps):
-    out = run(s)
+    graphs[s % ROT].replay()
 b.record()
 torch.cuda.synchronize()
+out = outs[0]
 ms = a.elapsed_time(b) / args.steps
 if world > 1:
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -75,7 +89,7 @@ if rank == 0:
         "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": prec, "data": "synthetic",
         "config": {"workload": "config3: multi_encoding_net forward, radii 0.5/1.0/1.5, nsample 256/256/512, mlp [64,128,256] x3, global batch 16 "
-                               "scenes sharded over the ranks", "scenes_per_rank": B, "seeds_per_scene": SEEDS},
+                               "scenes sharded over the ranks", "scenes_per_rank": B, "seeds_per_scene": SEEDS, "executor": "one CUDA graph per input set, replayed in order on one stream"},
         "mlp_gflop": flops / 1e9, "algorithmic_tflops": flops / (ms * 1e-3) / 1e12, "out_shape": list(out.shape)}))
 if world > 1:
     dist.destroy_process_group()
