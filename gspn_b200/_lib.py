@@ -42,6 +42,8 @@ SIGNATURES = {
     "gspn_grid_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gspn_grid_query_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gspn_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, P, P, P, P, P, c_size_t, P]),
+    "gspn_query_ball_point_multi": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    "gspn_ballquery_tune": (None, [c_int, c_int]),
     "gspn_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_grouped_bytes": (c_size_t, [c_long, c_int, c_int]),
@@ -49,6 +51,10 @@ SIGNATURES = {
     "gspn_three_nn": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_size_t, P]),
     "gspn_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "gspn_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P]),
+    "gspn_scatter_det_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gspn_gather_point_grad_det": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "gspn_group_point_grad_det": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "gspn_three_interpolate_grad_det": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     "gspn_nn_distance": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_int, P, c_size_t, P]),
     "gspn_nn_distance_grad": (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P, P]),
     "gspn_mlp_layer_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, c_int, c_int, P, P]),

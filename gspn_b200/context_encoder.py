@@ -14,6 +14,9 @@ from . import mlp_tc, ops
 from . import pointnet_util as pu
 
 
+FUSED_MULTI_RADIUS = True  # one ordered scan for all radii (False: one query_ball_point per radius, as the reference)
+
+
 def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list, mlp_list2, is_training, bn_decay, scope, bn=True,
                        use_xyz=False, output_shift=False, shift_pred=None, fps_idx=None, variables=None, precision=None):
     """-> (new_xyz (b,npoint,3), new_points (b,npoint,sum mlp[-1]), shift_pred, fps_idx)."""
@@ -32,12 +35,19 @@ def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list,
     c = 0 if points is None else points.shape[2]
     cin = c + 3 if (use_xyz or points is None) else c
     outs = []
+    all_layers = [store.layers(scope, "conv_prev_%d_" % i, cin, list(mlp), bn) for i, mlp in enumerate(mlp_list)]
+    # the nested balls share their seeds: when every radius goes through the in-chain gather, ONE scan finds all index lists
+    # (models/model_rpointnet.py:49-61 issues one query_ball_point per radius)
+    fused_idx = None
+    if (FUSED_MULTI_RADIUS and precision in pu.TC_PRECISIONS and mlp_tc.gather_ok(points) and 1 <= len(radius_list) <= 4
+            and all(mlp_tc.tc_supported(l, k) for l, k in zip(all_layers, nsample_list))):
+        fused_idx = [i_ for i_, _ in ops.query_ball_point_multi(radius_list, nsample_list, xyz, new_xyz)]
     for i, (radius, nsample, mlp) in enumerate(zip(radius_list, nsample_list, mlp_list)):
-        layers = store.layers(scope, "conv_prev_%d_" % i, cin, list(mlp), bn)
+        layers = all_layers[i]
         rows = b * m * nsample
         tc = precision in pu.TC_PRECISIONS and mlp_tc.tc_supported(layers, nsample)
         if tc and mlp_tc.gather_ok(points):
-            idx, _ = ops.query_ball_point(radius, nsample, xyz, new_xyz)
+            idx = fused_idx[i] if fused_idx is not None else ops.query_ball_point(radius, nsample, xyz, new_xyz)[0]
             perm = (list(range(c)) + ([c, c + 1, c + 2] if (use_xyz or points is None) else [-1, -1, -1]) + [-1] * (64 - c - 3))
             x = mlp_tc.mlp_chain_gather(xyz, new_xyz, shift_pred, points, idx, layers, perm, nsample, precision)  # validates its tensors
         elif tc:

@@ -208,6 +208,82 @@ __global__ void __launch_bounds__(kBQThreads) ballquery_kernel(int n, int m, flo
     }
 }
 
+// ---- several nested balls around the same queries in ONE ordered scan (multi_encoding_net, models/model_rpointnet.py:49-61: radii
+// 0.5 / 1.0 / 1.5 with nsample 256 / 256 / 512 around the same seeds).  A warp owns a query; the squared distance of a point is
+// computed once and compared with every ball's threshold; each ball keeps its own "first nsample in index order" list, and the scan
+// stops when all of them are full.  Results are bit-identical to one query_ball_point call per radius.
+constexpr int kBQMaxRadii = 4;
+struct MultiArgs {
+    float s_max[kBQMaxRadii];
+    int nsample[kBQMaxRadii];
+    int off[kBQMaxRadii];  // offset of ball r's index row inside a warp's shared-memory block
+    int *idx[kBQMaxRadii];
+    int *cnt[kBQMaxRadii];
+    int nrad, row_ints;
+};
+
+__global__ void __launch_bounds__(kBQThreads) ballquery_multi_kernel(int n, int m, const float *__restrict__ xyz1, const float *__restrict__ xyz2,
+                                                                     const MultiArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);                   // [2][kBQTile*3]
+    int *widx = reinterpret_cast<int *>(smem_raw + 2 * kBQTile * 3 * 4);  // [kBQWarps][row_ints]
+    const int cloud = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *p = xyz1 + (size_t)cloud * n * 3;
+    const int j = blockIdx.x * kBQWarps + warp;
+    const bool mine = j < m;
+    const float *q = xyz2 + ((size_t)cloud * m + (mine ? j : 0)) * 3;
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    int cnt[kBQMaxRadii];
+#pragma unroll
+    for (int r = 0; r < kBQMaxRadii; ++r) cnt[r] = (mine && r < a.nrad) ? 0 : 0x7fffffff;  // absent balls are born full
+    int *myidx = widx + (size_t)warp * a.row_ints;
+    bool active = mine;
+    const int ntiles = ceil_div(n, kBQTile);
+    for (int t = 0; t < ntiles; ++t) {
+        const int k0 = t * kBQTile;
+        const int cntp = min(kBQTile, n - k0);
+        float *tile = tiles + (size_t)(t & 1) * kBQTile * 3;
+        for (int e = threadIdx.x; e < cntp * 3; e += kBQThreads) tile[e] = __ldg(p + (size_t)k0 * 3 + e);
+        __syncthreads();
+        if (active) {
+            for (int base = 0; base < cntp; base += 32) {
+                const int kl = base + lane;
+                const bool valid = kl < cntp;
+                const int ks = valid ? kl : 0;
+                const float s = sqdist_fma(qx, qy, qz, tile[3 * ks], tile[3 * ks + 1], tile[3 * ks + 2]);
+                bool alldone = true;
+#pragma unroll
+                for (int r = 0; r < kBQMaxRadii; ++r) {
+                    if (cnt[r] < a.nsample[r]) {  // warp-uniform; absent balls never enter
+                        const bool hit = valid && !(s > a.s_max[r]);
+                        const unsigned bal = __ballot_sync(GSPN_FULL_MASK, hit);
+                        if (bal) {
+                            const int pos = cnt[r] + __popc(bal & ((1u << lane) - 1u));
+                            if (hit && pos < a.nsample[r]) myidx[a.off[r] + pos] = k0 + kl;
+                            cnt[r] = min(a.nsample[r], cnt[r] + __popc(bal));
+                        }
+                        alldone &= (cnt[r] >= a.nsample[r]);
+                    }
+                }
+                if (alldone) { active = false; break; }
+            }
+        }
+        if (__syncthreads_or(active ? 1 : 0) == 0) break;  // tile buffer reuse + CTA-wide early exit
+    }
+    __syncwarp();
+    if (!mine) return;
+#pragma unroll
+    for (int r = 0; r < kBQMaxRadii; ++r) {
+        if (r >= a.nrad) continue;
+        const int ns = a.nsample[r], cn = cnt[r];
+        const int first = cn > 0 ? myidx[a.off[r]] : 0;  // zero-hit row: zeros (reference leaves it unwritten)
+        int *dst = a.idx[r] + ((size_t)cloud * m + j) * ns;
+        for (int l = lane; l < ns; l += 32) dst[l] = l < cn ? myidx[a.off[r] + l] : first;  // back-fill with the first hit (:29-32)
+        if (lane == 0) a.cnt[r][(size_t)cloud * m + j] = cn;
+    }
+}
+
 }  // namespace gspn
 
 using namespace gspn;
@@ -218,6 +294,9 @@ int gspn_ballquery_grid_launch(int b, int n, int m, float radius, int nsample, c
 extern "C" size_t gspn_grid_workspace_bytes(int b, int n);
 constexpr int kGridMinPoints = 4096;  // below this the brute-force scan is already a few microseconds
 
+static int g_bq_qpw = 0, g_bq_qpc = 0;  // tuning doors: queries per warp / per CTA of the ordered-scan kernel (0 = choose)
+extern "C" void gspn_ballquery_tune(int queries_per_warp, int queries_per_cta) { g_bq_qpw = queries_per_warp; g_bq_qpc = queries_per_cta; }
+
 static int launch_ballquery(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2, int *idx, int *pts_cnt,
                             GroupArgs g, cudaStream_t s) {
     const float s_max = ball_threshold(radius);
@@ -225,10 +304,7 @@ static int launch_ballquery(int b, int n, int m, float radius, int nsample, cons
     // as long as one 8-warp CTA per SM remains
     long warps1 = (long)b * m;
     int qpw = warps1 >= 148L * 8 * 4 ? 2 : 1;  // measured (tools/op_bench.py): 2 beats 1 and 4 on 8 x 32768 -> 2048
-    if (const char *e = getenv("GSPN_BQ_QPW")) {  // tuning door (tools/op_bench.py)
-        int v = atoi(e);
-        if (v == 1 || v == 2 || v == 4) qpw = v;
-    }
+    if (g_bq_qpw == 1 || g_bq_qpw == 2 || g_bq_qpw == 4) qpw = g_bq_qpw;  // tuning door (gspn_ballquery_tune)
     if ((size_t)qpw * nsample * 4 * kBQWarps > 96 * 1024) qpw = 1;
     size_t smem = (size_t)2 * kBQTile * 3 * 4 + (size_t)kBQWarps * qpw * nsample * 4;
     if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;
@@ -240,10 +316,7 @@ static int launch_ballquery(int b, int n, int m, float radius, int nsample, cons
     if (g.grouped && g.ld >= 64 && n <= 1024) {
         while (qpc > 1 && (long)b * ceil_div(m, qpc) < 148L * 4) qpc >>= 1;
     }
-    if (const char *e = getenv("GSPN_BQ_QPC")) {
-        int v = atoi(e);
-        if (v >= 1 && v <= kBQWarps * qpw) qpc = v;
-    }
+    if (g_bq_qpc >= 1 && g_bq_qpc <= kBQWarps * qpw) qpc = g_bq_qpc;
     dim3 grid(ceil_div(m, qpc), b);
 #define GSPN_BQ_LAUNCH(Q)                                                                                                       \
     do {                                                                                                                        \
@@ -269,6 +342,37 @@ extern "C" int gspn_query_ball_point(int b, int n, int m, float radius, int nsam
         return gspn_ballquery_grid_launch(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, g, workspace, as_stream(stream));
     }
     return launch_ballquery(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, g, as_stream(stream));
+}
+
+extern "C" int gspn_query_ball_point_multi(int b, int n, int m, int nrad, const float *radii, const int *nsamples, const float *xyz1,
+                                           const float *xyz2, int *const *idx, int *const *pts_cnt, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n > 0 && m >= 0 && b <= 65535 && nrad >= 1 && nrad <= kBQMaxRadii);
+    GSPN_REQUIRE_PTR(radii); GSPN_REQUIRE_PTR(nsamples); GSPN_REQUIRE_PTR(idx); GSPN_REQUIRE_PTR(pts_cnt);
+    if (b == 0 || m == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(xyz1); GSPN_REQUIRE_PTR(xyz2);
+    MultiArgs a = {};
+    a.nrad = nrad;
+    int off = 0;
+    for (int r = 0; r < kBQMaxRadii; ++r) {
+        if (r < nrad) {
+            GSPN_REQUIRE(radii[r] > 0.f && nsamples[r] > 0);  // tf_grouping.cpp:101,104
+            GSPN_REQUIRE_PTR(idx[r]); GSPN_REQUIRE_PTR(pts_cnt[r]);
+            a.s_max[r] = ball_threshold(radii[r]);
+            a.nsample[r] = nsamples[r];
+            a.off[r] = off;
+            a.idx[r] = idx[r]; a.cnt[r] = pts_cnt[r];
+            off += nsamples[r];
+        } else {
+            a.s_max[r] = -1.f; a.nsample[r] = 0; a.off[r] = 0;
+        }
+    }
+    a.row_ints = off;
+    const size_t smem = (size_t)2 * kBQTile * 3 * 4 + (size_t)kBQWarps * off * 4;
+    if (smem > 200 * 1024) return GSPN_E_UNSUPPORTED;
+    GSPN_CUDA_OK(cudaFuncSetAttribute(ballquery_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(m, kBQWarps), b);
+    ballquery_multi_kernel<<<grid, kBQThreads, smem, as_stream(stream)>>>(n, m, xyz1, xyz2, a);
+    return check_launch();
 }
 
 extern "C" size_t gspn_grouped_bytes(long rows, int c_plus_xyz, int grouped_dtype) {

@@ -186,6 +186,56 @@ __global__ void __launch_bounds__(kThreads) nn_distance_grad_kernel(long total, 
     }
 }
 
+// ---- deterministic scatter-add (the reference's backward ops add with atomics in whatever order the hardware picks:
+// tf_sampling_g.cu:183-192, tf_grouping_g.cu:66-83, and its CPU ThreeInterpolateGrad sums in index order).  Float addition does
+// not commute in rounding, integer addition does: every contribution is scaled by a power of two chosen from the largest
+// |contribution| and the number of entries per cloud, rounded to a 64-bit integer and added with integer atomics; the sum is
+// converted back at the end.  Bit-reproducible from run to run and order-independent; the quantisation step is 2^-(61 - log2(E))
+// of the largest contribution, far below fp32 round-off.  One generic kernel set serves gather / group / three_interpolate:
+//   dst[b, idx[b, e], :] += weight[b, e] * src[b, e / rep, :]      e = 0 .. E-1 per cloud (rep = 3 for three_interpolate)
+__global__ void __launch_bounds__(kThreads) det_absmax_kernel(long total, int c, int rep, const float *__restrict__ src,
+                                                              const float *__restrict__ weight, unsigned *__restrict__ amax_bits) {
+    float mx = 0.f;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long ent = e / c;  // global entry index b*E + e
+        const int l = (int)(e - ent * c);
+        const float v = __ldg(src + (ent / rep) * c + l) * (weight ? __ldg(weight + ent) : 1.f);
+        mx = fmaxf(mx, fabsf(v));
+    }
+    mx = __uint_as_float(__reduce_max_sync(GSPN_FULL_MASK, __float_as_uint(mx)));  // non-negative floats order as unsigned ints
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(amax_bits, __float_as_uint(mx));
+}
+__device__ __forceinline__ float det_scale(unsigned amax_bits, long entries_per_cloud) {
+    // 2^k with  amax * entries * 2^k < 2^62 ; amax == 0 (all-zero gradient) -> any scale works
+    const float amax = __uint_as_float(amax_bits);
+    int ea = 0;
+    if (amax > 0.f && amax < 3e38f) frexpf(amax, &ea);  // amax < 2^ea
+    int ee = 0;
+    while ((1L << ee) < entries_per_cloud) ++ee;
+    int k = 61 - ea - ee;
+    k = k > 126 ? 126 : (k < -126 ? -126 : k);
+    return ldexpf(1.0f, k);
+}
+__global__ void __launch_bounds__(kThreads) det_scatter_kernel(long total, int n_dst, long E, int c, int rep, const float *__restrict__ src,
+                                                               const int *__restrict__ idx, const float *__restrict__ weight,
+                                                               const unsigned *__restrict__ amax_bits, long long *__restrict__ acc) {
+    const float scale = det_scale(*amax_bits, E);
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long ent = e / c;
+        const int l = (int)(e - ent * c);
+        const long bi = ent / E;
+        const float v = __fmul_rn(__ldg(src + (ent / rep) * c + l), weight ? __ldg(weight + ent) : 1.f);  // the contribution, rounded as the op rounds it
+        const long long q = __float2ll_rn(v * scale);  // exact scaling by a power of two, then ONE rounding to the integer grid
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + (bi * n_dst + __ldg(idx + ent)) * c + l, (unsigned long long)q);
+    }
+}
+__global__ void __launch_bounds__(kThreads) det_finish_kernel(long total, long E, const unsigned *__restrict__ amax_bits,
+                                                              const long long *__restrict__ acc, float *__restrict__ dst) {
+    const float inv = 1.0f / det_scale(*amax_bits, E);
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+        dst[e] = (float)((double)acc[e] * (double)inv);
+}
+
 // box_shrink (models/model_rpointnet.py:529-551): tighten every box to the points it contains.  One warp per box; the
 // reference's "large number" trick is kept verbatim (outside points are shifted by -/+ gamma = 1e4 before the max / min over ALL
 // points), so an empty box yields max - min < 0 and is zeroed exactly as there.
@@ -371,3 +421,45 @@ extern "C" int gspn_box_shrink(int b, int nbox, int n, const float *box, const f
     return check_launch();
 }
 
+
+// ---- deterministic forms of the backward ops (see det_scatter_kernel) ---------------------------------------------------------
+extern "C" size_t gspn_scatter_det_workspace_bytes(int b, int n_dst, int c) {
+    if (b <= 0 || n_dst <= 0 || c <= 0) return 0;
+    return 256 + sizeof(long long) * (size_t)b * n_dst * c;
+}
+
+static int scatter_det(int b, int n_dst, long E, int c, int rep, const float *src, const int *idx, const float *weight, float *dst,
+                       void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
+    GSPN_REQUIRE(b >= 0 && n_dst > 0 && c > 0 && E >= 0);
+    if (b == 0) return GSPN_OK;
+    GSPN_REQUIRE_PTR(dst);
+    cudaStream_t st = as_stream(stream);
+    const long ndst = (long)b * n_dst * c;
+    if (E == 0) { GSPN_CUDA_OK(cudaMemsetAsync(dst, 0, sizeof(float) * ndst, st)); return GSPN_OK; }
+    GSPN_REQUIRE_PTR(src); GSPN_REQUIRE_PTR(idx);
+    if (workspace == nullptr || workspace_bytes < gspn_scatter_det_workspace_bytes(b, n_dst, c)) return GSPN_E_WORKSPACE;
+    unsigned *amax = reinterpret_cast<unsigned *>(workspace);
+    long long *acc = reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(workspace) + 256);
+    GSPN_CUDA_OK(cudaMemsetAsync(workspace, 0, 256 + sizeof(long long) * (size_t)ndst, st));
+    const long total = (long)b * E * c;
+    det_absmax_kernel<<<blocks_for(total), kThreads, 0, st>>>(total, c, rep, src, weight, amax);
+    det_scatter_kernel<<<blocks_for(total), kThreads, 0, st>>>(total, n_dst, E, c, rep, src, idx, weight, amax, acc);
+    det_finish_kernel<<<blocks_for(ndst), kThreads, 0, st>>>(ndst, E, amax, acc, dst);
+    return check_launch();
+}
+
+extern "C" int gspn_gather_point_grad_det(int b, int n, int m, int c, const float *out_g, const int *idx, float *inp_g, void *workspace,
+                                          size_t workspace_bytes, gspn_stream_t stream) {
+    return scatter_det(b, n, m, c, 1, out_g, idx, nullptr, inp_g, workspace, workspace_bytes, stream);
+}
+extern "C" int gspn_group_point_grad_det(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx, float *grad_points,
+                                         void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
+    GSPN_REQUIRE(m >= 0 && nsample > 0);
+    return scatter_det(b, n, (long)m * nsample, c, 1, grad_out, idx, nullptr, grad_points, workspace, workspace_bytes, stream);
+}
+extern "C" int gspn_three_interpolate_grad_det(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight,
+                                               float *grad_points, void *workspace, size_t workspace_bytes, gspn_stream_t stream) {
+    GSPN_REQUIRE(n >= 0);
+    if (b > 0 && n > 0) GSPN_REQUIRE_PTR(weight);
+    return scatter_det(b, m, (long)n * 3, c, 3, grad_out, idx, weight, grad_points, workspace, workspace_bytes, stream);
+}

@@ -55,6 +55,14 @@ def _p(t):
 
 
 GRID_SEARCH = True  # exact uniform-grid neighbour search for large clouds (False: always the O(n*m) scans)
+# Backward of gather_point / group_point / three_interpolate: False = float atomics like the reference's kernels (gradients differ
+# in the last bits from run to run), True = the order-independent integer accumulation (bit-reproducible; include/gspn_b200.h).
+DETERMINISTIC_BACKWARD = False
+
+
+def _det_ws(b, n_dst, c, dev):
+    nbytes = _lib.lib().gspn_scatter_det_workspace_bytes(b, n_dst, c)
+    return torch.empty((nbytes,), dtype=torch.uint8, device=dev), nbytes
 
 
 def _grid_ws(b, n_scanned, dev, min_points):
@@ -105,7 +113,11 @@ class _GatherPoint(torch.autograd.Function):
         out_g = out_g.contiguous()
         b, m, c = out_g.shape
         inp_g = torch.empty((b, ctx.n, c), dtype=torch.float32, device=out_g.device)
-        check(_lib.lib().gspn_gather_point_grad(b, ctx.n, m, c, _p(out_g), _p(idx), _p(inp_g), _stream()), "gather_point_grad")
+        if DETERMINISTIC_BACKWARD:
+            ws, wsb = _det_ws(b, ctx.n, c, out_g.device)
+            check(_lib.lib().gspn_gather_point_grad_det(b, ctx.n, m, c, _p(out_g), _p(idx), _p(inp_g), _p(ws), wsb, _stream()), "gather_point_grad_det")
+        else:
+            check(_lib.lib().gspn_gather_point_grad(b, ctx.n, m, c, _p(out_g), _p(idx), _p(inp_g), _stream()), "gather_point_grad")
         return inp_g, None
 
 
@@ -134,6 +146,31 @@ def query_ball_point(radius, nsample, xyz1, xyz2):
     return idx, cnt
 
 
+def query_ball_point_multi(radius_list, nsample_list, xyz1, xyz2):
+    """Several nested balls around the same queries in one scan (multi_encoding_net, models/model_rpointnet.py:49-61).
+    -> [(idx_r (b,m,nsample_r) i32, pts_cnt_r (b,m) i32) for every radius]; bit-identical to query_ball_point per radius."""
+    import ctypes
+    _req(len(radius_list) == len(nsample_list) and 1 <= len(radius_list) <= 4, "query_ball_point_multi takes 1..4 (radius, nsample) pairs")
+    _req(all(r > 0 for r in radius_list), "QueryBallPoint expects positive radius")
+    _req(all(k > 0 for k in nsample_list), "QueryBallPoint expects positive nsample")
+    _req(xyz1.dim() == 3 and xyz1.shape[2] == 3, "QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape.")
+    _req(xyz2.dim() == 3 and xyz2.shape[2] == 3, "QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape.")
+    xyz1, xyz2 = _cuda_f32(xyz1.detach(), "xyz1"), _cuda_f32(xyz2.detach(), "xyz2")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    nr = len(radius_list)
+    idxs = [torch.empty((b, m, k), dtype=torch.int32, device=xyz1.device) for k in nsample_list]
+    cnts = [torch.empty((b, m), dtype=torch.int32, device=xyz1.device) for _ in nsample_list]
+    rad = (ctypes.c_float * nr)(*[float(r) for r in radius_list])
+    ns = (ctypes.c_int * nr)(*[int(k) for k in nsample_list])
+    pi = (ctypes.c_void_p * nr)(*[t.data_ptr() for t in idxs])
+    pc = (ctypes.c_void_p * nr)(*[t.data_ptr() for t in cnts])
+    c = ctypes.cast
+    check(_lib.lib().gspn_query_ball_point_multi(b, n, m, nr, c(rad, ctypes.c_void_p), c(ns, ctypes.c_void_p), _p(xyz1), _p(xyz2),
+                                                 c(pi, ctypes.c_void_p), c(pc, ctypes.c_void_p), _stream()), "query_ball_point_multi")
+    return list(zip(idxs, cnts))
+
+
 class _GroupPoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, idx):
@@ -151,7 +188,11 @@ class _GroupPoint(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         b, m, k, c = grad_out.shape
         g = torch.empty((b, ctx.n, c), dtype=torch.float32, device=grad_out.device)
-        check(_lib.lib().gspn_group_point_grad(b, ctx.n, c, m, k, _p(grad_out), _p(idx), _p(g), _stream()), "group_point_grad")
+        if DETERMINISTIC_BACKWARD:
+            ws, wsb = _det_ws(b, ctx.n, c, grad_out.device)
+            check(_lib.lib().gspn_group_point_grad_det(b, ctx.n, c, m, k, _p(grad_out), _p(idx), _p(g), _p(ws), wsb, _stream()), "group_point_grad_det")
+        else:
+            check(_lib.lib().gspn_group_point_grad(b, ctx.n, c, m, k, _p(grad_out), _p(idx), _p(g), _stream()), "group_point_grad")
         return g, None
 
 
@@ -196,8 +237,13 @@ class _ThreeInterpolate(torch.autograd.Function):
         grad_out = grad_out.contiguous()
         b, n, c = grad_out.shape
         g = torch.empty((b, ctx.m, c), dtype=torch.float32, device=grad_out.device)
-        check(_lib.lib().gspn_three_interpolate_grad(b, n, c, ctx.m, _p(grad_out), _p(idx), _p(weight), _p(g), _stream()),
-              "three_interpolate_grad")
+        if DETERMINISTIC_BACKWARD:
+            ws, wsb = _det_ws(b, ctx.m, c, grad_out.device)
+            check(_lib.lib().gspn_three_interpolate_grad_det(b, n, c, ctx.m, _p(grad_out), _p(idx), _p(weight), _p(g), _p(ws), wsb, _stream()),
+                  "three_interpolate_grad_det")
+        else:
+            check(_lib.lib().gspn_three_interpolate_grad(b, n, c, ctx.m, _p(grad_out), _p(idx), _p(weight), _p(g), _stream()),
+                  "three_interpolate_grad")
         return g, None, None  # tf_interpolate.py:34
 
 

@@ -123,6 +123,14 @@ size_t gspn_grid_workspace_bytes(int b, int npoints_scanned);
 size_t gspn_grid_query_workspace_bytes(int b, int n_queries, int npoints_scanned);
 int gspn_query_ball_point(int b, int n, int m, float radius, int nsample, const float *xyz1, const float *xyz2,
                           int *idx, int *pts_cnt, void *workspace, size_t workspace_bytes, gspn_stream_t stream);
+/* Several nested balls around the same queries in ONE ordered scan (multi_encoding_net, models/model_rpointnet.py:49-61: three
+ * query_ball_point calls with radii 0.5 / 1.0 / 1.5 around the same seeds).  radii / nsamples / idx / pts_cnt are HOST arrays of
+ * nrad (<= 4) entries; idx[r] (b,m,nsamples[r]) and pts_cnt[r] (b,m) are device buffers.  Bit-identical to nrad calls of
+ * gspn_query_ball_point. */
+int gspn_query_ball_point_multi(int b, int n, int m, int nrad, const float *radii, const int *nsamples, const float *xyz1,
+                                const float *xyz2, int *const *idx, int *const *pts_cnt, gspn_stream_t stream);
+/* Tuning door (process-wide): queries per warp (1, 2, 4) / per CTA of the ordered-scan ball query; 0 = choose. */
+void gspn_ballquery_tune(int queries_per_warp, int queries_per_cta);
 /* group_point(points, idx)  tf_grouping.py:54-62; groupPointLauncher tf_grouping_g.cu:194
  * points (b,n,c), idx (b,m,nsample) -> out (b,m,nsample,c). */
 int gspn_group_point(int b, int n, int c, int m, int nsample, const float *points, const int *idx, float *out, gspn_stream_t stream);
@@ -163,6 +171,19 @@ int gspn_three_interpolate(int b, int m, int c, int n, const float *points, cons
 /* ThreeInterpolateGrad  tf_interpolate.py:29-34; threeinterpolate_grad_cpu tf_interpolate.cpp:131
  * grad_out (b,n,c) -> grad_points (b,m,c) (zeroed here). */
 int gspn_three_interpolate_grad(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points, gspn_stream_t stream);
+
+/* Deterministic forms of the scatter-add backward ops (GatherPointGrad, GroupPointGrad, ThreeInterpolateGrad): the reference's GPU
+ * kernels add with float atomics in hardware order (tf_sampling_g.cu:183-192, tf_grouping_g.cu:66-83), so its gradients differ from
+ * run to run in the last bits.  Here every contribution is scaled by a power of two, rounded to a 64-bit integer and added with integer
+ * atomics (integer addition is associative): bit-reproducible, order-independent, quantisation far below fp32 round-off.
+ * workspace: gspn_scatter_det_workspace_bytes(b, rows of the gradient being written, c). */
+size_t gspn_scatter_det_workspace_bytes(int b, int n_dst, int c);
+int gspn_gather_point_grad_det(int b, int n, int m, int c, const float *out_g, const int *idx, float *inp_g, void *workspace,
+                               size_t workspace_bytes, gspn_stream_t stream);
+int gspn_group_point_grad_det(int b, int n, int c, int m, int nsample, const float *grad_out, const int *idx, float *grad_points,
+                              void *workspace, size_t workspace_bytes, gspn_stream_t stream);
+int gspn_three_interpolate_grad_det(int b, int n, int c, int m, const float *grad_out, const int *idx, const float *weight,
+                                    float *grad_points, void *workspace, size_t workspace_bytes, gspn_stream_t stream);
 
 /* --------------------------------------------------------------- nn_distance
  * nn_distance(xyz1, xyz2)  tf_ops/nn_distance/tf_nndistance.py:14-24

@@ -1061,3 +1061,79 @@ def test_one_process_driving_two_devices(cuda, oracle):
             outs.append((N(out), N(idx)))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][1], oracle.farthest_point_sample(300, xyz))
+
+
+def test_query_ball_point_multi_equals_one_call_per_radius(cuda, oracle):
+    """models/model_rpointnet.py:49-61: three nested balls around the same seeds found by ONE scan -- identical to three calls."""
+    xyz = scenes.with_duplicates(scenes.scannet_like_batch(60, 2, 9000)[0], 0.1)
+    x = T(xyz, cuda)
+    seeds = gspn_b200.gather_point(x, gspn_b200.farthest_point_sample(70, x))
+    for radii, ks in (([0.5, 1.0, 1.5], [256, 256, 512]), ([0.05], [8]), ([0.3, 0.3001, 2.0, 50.0], [16, 300, 7, 64])):
+        got = ops.query_ball_point_multi(radii, ks, x, seeds)
+        for (gi, gc), r, k in zip(got, radii, ks):
+            ei, ec = gspn_b200.query_ball_point(r, k, x, seeds)
+            assert torch.equal(gi, ei) and torch.equal(gc, ec), (r, k)
+    oi, oc = oracle.query_ball_point(0.5, 256, xyz[:1], N(seeds)[:1])
+    gi, gc = ops.query_ball_point_multi([0.5, 1.0], [256, 64], x, seeds)[0]
+    assert np.array_equal(N(gi)[:1], oi) and np.array_equal(N(gc)[:1], oc)
+
+
+def test_multi_encoding_net_fused_scan_equals_per_radius(cuda):
+    from gspn_b200 import context_encoder
+    xyz, col = scenes.scannet_like_batch(71, 2, 8192)
+    x, c = T(xyz, cuda), T(col, cuda)
+    fps = gspn_b200.farthest_point_sample(32, x)
+    st = pu.VariableStore(device=cuda)
+    args = (x, c, 32, [0.5, 1.0, 1.5], [64, 64, 128], [[64, 128, 256]] * 3, [], False, None, "ctxf")
+    a = context_encoder.multi_encoding_net(*args, use_xyz=True, fps_idx=fps, variables=st)[1]
+    context_encoder.FUSED_MULTI_RADIUS = False
+    try:
+        b_ = context_encoder.multi_encoding_net(*args, use_xyz=True, fps_idx=fps, variables=st)[1]
+    finally:
+        context_encoder.FUSED_MULTI_RADIUS = True
+    assert torch.equal(a, b_)
+
+
+def test_deterministic_backward_is_reproducible_and_accurate(cuda, oracle):
+    """ops.DETERMINISTIC_BACKWARD: integer accumulation instead of float atomics -- bit-identical from run to run (heavy collisions:
+    many rows scatter into few), and within 1e-6 of the float64 sum (the reference's own gradient tests allow 1e-4)."""
+    rng = np.random.RandomState(31)
+    b, n, m, k, c = 2, 300, 4000, 16, 35
+    idx = T(rng.randint(0, 40, size=(b, m, k)).astype(np.int32), cuda)      # 64000 rows into 40 targets per cloud
+    go = T(rng.randn(b, m, k, c).astype(np.float32) * 3.0, cuda)
+    pts = torch.zeros((b, n, c), device=cuda, requires_grad=True)
+    idx3 = T(rng.randint(0, 25, size=(b, 5000, 3)).astype(np.int32), cuda)
+    w3 = T(rng.rand(b, 5000, 3).astype(np.float32), cuda)
+    go3 = T(rng.randn(b, 5000, c).astype(np.float32), cuda)
+    gidx = T(rng.randint(0, 10, size=(b, 7000)).astype(np.int32), cuda)
+    gog = T(rng.randn(b, 7000, c).astype(np.float32), cuda)
+
+    def grads():
+        out = []
+        p = pts.detach().clone().requires_grad_(True)
+        gspn_b200.group_point(p, idx).backward(go)
+        out.append(p.grad.clone())
+        p = pts.detach().clone().requires_grad_(True)
+        gspn_b200.three_interpolate(p, idx3, w3).backward(go3)
+        out.append(p.grad.clone())
+        p = pts.detach().clone().requires_grad_(True)
+        gspn_b200.gather_point(p, gidx).backward(gog)
+        out.append(p.grad.clone())
+        return out
+    ops.DETERMINISTIC_BACKWARD = True
+    try:
+        runs = [grads() for _ in range(3)]
+    finally:
+        ops.DETERMINISTIC_BACKWARD = False
+    for r in runs[1:]:
+        for a, b_ in zip(runs[0], r):
+            assert torch.equal(a, b_)  # bit-reproducible
+    # float64 references
+    e0 = np.zeros((b, n, c)); np.add.at(e0, (np.arange(b)[:, None, None], N(idx)), N(go).astype(np.float64))
+    e1 = np.zeros((b, n, c)); np.add.at(e1, (np.arange(b)[:, None, None], N(idx3)), (N(go3).astype(np.float64)[:, :, None, :] * N(w3).astype(np.float32)[..., None].astype(np.float64)))
+    e2 = np.zeros((b, n, c)); np.add.at(e2, (np.arange(b)[:, None], N(gidx)), N(gog).astype(np.float64))
+    for got, exp in zip(runs[0], (e0, e1, e2)):
+        np.testing.assert_allclose(N(got), exp, rtol=1e-6, atol=1e-6 * np.abs(exp).max())
+    atomics = grads()  # and the default (float atomics) agrees within the reference's own tolerance
+    for a, exp in zip(atomics, (e0, e1, e2)):
+        np.testing.assert_allclose(N(a), exp, rtol=1e-4, atol=1e-4 * np.abs(exp).max())

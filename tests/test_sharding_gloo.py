@@ -72,7 +72,7 @@ def _grad_worker(rank, world, port, q):
     params = [torch.zeros(3, 4), torch.zeros(5), torch.zeros(2, 2)]
     for i, p in enumerate(params):
         p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
-    params[2].grad = None  # parameters without a gradient are skipped consistently on every rank
+    params[2].grad = None  # a parameter without a gradient contributes zeros: the bucket has the same size on every rank
     allreduce_gradients(params)
     if rank == 0:
         q.put([None if p.grad is None else p.grad.flatten()[0].item() for p in params])
@@ -91,4 +91,4 @@ def test_gradient_allreduce_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert got == [1.5, 3.0, None]  # mean over ranks of (rank+1)*(i+1)
+    assert got == [1.5, 3.0, 0.0]  # mean over ranks of (rank+1)*(i+1); zeros where no rank had a gradient

@@ -27,6 +27,10 @@ name_i = ci["Kernel Name"]
 out = [["Kernel Name"] + COLS, [""] + [units[ci[c]] if c in ci else "" for c in COLS]]
 traffic = {}
 count = {"fps": 0, "bq": 0, "chain": 0, "nn": 0, "asm": 0}
+# launch order of one forward (backbone.forward, default precision): SA1..4: fps, [grid build], ball query(+group), chain;
+# FP1..3: three_nn, fp_assemble, chain; FP4: three_nn, fp_assemble (rows -> image), chain (y2 = points2 @ W0[:c2]), chain (gather + layers 1..)
+CHAIN_STAGE = {1: "layer1:mlp", 2: "layer2:mlp", 3: "layer3:mlp", 4: "layer4:mlp", 5: "fa_layer1:mlp", 6: "fa_layer2:mlp", 7: "fa_layer3:mlp",
+               8: "fa_layer4:interpolate", 9: "fa_layer4:mlp"}
 for r in data:
     name = r[name_i]
     out.append([name[:60]] + [r[ci[c]] if c in ci else "" for c in COLS])
@@ -37,7 +41,7 @@ for r in data:
         count["bq"] += 1; stage = "layer%d:ballquery_group" % count["bq"]
     elif "mlp_chain" in name:
         count["chain"] += 1
-        stage = ("layer%d:mlp" % count["chain"]) if count["chain"] <= 4 else ("fa_layer%d:mlp" % (count["chain"] - 4))
+        stage = CHAIN_STAGE.get(count["chain"])
     elif "three_nn" in name:
         count["nn"] += 1; stage = "fa_layer%d:three_nn" % count["nn"]
     elif "fp_assemble" in name:
@@ -45,9 +49,11 @@ for r in data:
     if stage:
         rd = to_bytes(r[ci["dram__bytes_read.sum"]], units[ci["dram__bytes_read.sum"]])
         wr = to_bytes(r[ci["dram__bytes_write.sum"]], units[ci["dram__bytes_write.sum"]])
-        traffic[stage] = {"dram_read_bytes": int(rd), "dram_write_bytes": int(wr), "traffic_bytes": int(rd + wr),
-                          "ncu_duration_ms": round(to_ms(r[ci["gpu__time_duration.sum"]], units[ci["gpu__time_duration.sum"]]), 6),
-                          "kernel": name[:60]}
+        dur = to_ms(r[ci["gpu__time_duration.sum"]], units[ci["gpu__time_duration.sum"]])
+        t = traffic.setdefault(stage, {"dram_read_bytes": 0, "dram_write_bytes": 0, "traffic_bytes": 0, "ncu_duration_ms": 0.0, "kernel": ""})
+        t["dram_read_bytes"] += int(rd); t["dram_write_bytes"] += int(wr); t["traffic_bytes"] += int(rd + wr)
+        t["ncu_duration_ms"] = round(t["ncu_duration_ms"] + dur, 6)
+        t["kernel"] = (t["kernel"] + " + " if t["kernel"] else "") + name[:60]
 csv.writer(open(sys.argv[2], "w")).writerows(out)
 json.dump(traffic, open(sys.argv[3], "w"), indent=1)
 print("kernels", len(data), "stages", len(traffic))

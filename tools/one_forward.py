@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gspn_b200 import backbone, scenes
 dev = torch.device("cuda:0")
-prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+prec = sys.argv[1] if len(sys.argv) > 1 else None  # None = the default precision (bf16x3)
 xyz, col = scenes.scannet_like_batch(0, 8, 32768)
 x, c = torch.from_numpy(xyz).to(dev), torch.from_numpy(col).to(dev)
 store, _ = backbone.random_variables(dev)
