@@ -204,13 +204,19 @@ class StageTimers:
         return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.ev.items()}
 
 
+def _r16(k):
+    return ((k + 15) // 16) * 16  # k-slices of 16 columns: what the chain kernel actually multiplies
+
+
 PAIR_FLOPS = 8  # one point-pair evaluation: 3 FSUB + FMUL + 2 FFMA (FMA = 2 flops); the compare / select is not counted
 
 
 def stage_costs(B, precision):
     """Algorithmic bytes / flops / pair evaluations per launch of each stage (SURVEY.md 8d formulas; DESIGN.md 'Measurement').
-    -> name -> (bound, amount[, pair_evals]): "hbm" bytes, "tensor" flops; the search stages (FPS, ball query, three_nn) also carry the
-    O(n*m) pair evaluations of the reference's scan -- the work an exact method has to be equivalent to -- for the FP32 roofline."""
+    -> name -> (bound, amount[, pair_evals[, issued]]): "hbm" bytes, "tensor" flops (ALGORITHMIC: the module's layers as the reference
+    computes them); the search stages (FPS, ball query, three_nn) also carry the O(n*m) pair evaluations of the reference's scan -- the
+    work an exact method has to be equivalent to -- for the FP32 roofline; tensor stages carry the flops of the MMAs actually ISSUED per
+    bf16 pass (k-slices of 16 columns; the commuted feature-propagation form issues fewer than the algorithm has)."""
     from gspn_b200 import backbone
     tc = precision in ("bf16", "bf16x3")
     e_img = {"bf16": 2, "bf16x3": 4}.get(precision, 4)  # bytes per element of the grouped rows the search stage writes
@@ -230,7 +236,8 @@ def stage_costs(B, precision):
         else:
             costs[s + ":ballquery_group"] = ("hbm", B * (12 * n + 12 * m + n * c * 4 + 4 * m * k + 4 * m + m * k * ld * e_img), B * m * n)
         dims = [c + 3] + mlp
-        costs[s + ":mlp"] = ("tensor", 2 * B * m * k * sum(a * b for a, b in zip(dims, dims[1:])))
+        costs[s + ":mlp"] = ("tensor", 2 * B * m * k * sum(a * b for a, b in zip(dims, dims[1:])), None,
+                             2 * B * m * k * sum(_r16(a) * b for a, b in zip(dims, dims[1:])))
         n, c = m, mlp[-1]
         chans.append(c)
         ns.append(n)
@@ -241,9 +248,16 @@ def stage_costs(B, precision):
         n1, m2, c1 = ns[lvl], ns[lvl + 1], chans[lvl]
         costs[s + ":three_nn"] = ("hbm", B * (12 * n1 + 12 * m2 + 36 * n1), B * n1 * m2)
         # three_interpolate + concat as the reference runs them: idx + weight + the known features once + the interpolated map
-        costs[s + ":interpolate"] = ("hbm", B * (24 * n1 + m2 * up * 4 + n1 * (up + c1) * e_img + n1 * c1 * 4))
         dims = [up + c1] + mlp
-        costs[s + ":mlp"] = ("tensor", 2 * B * n1 * sum(a * b for a, b in zip(dims, dims[1:])))
+        flops = 2 * B * n1 * sum(a * b for a, b in zip(dims, dims[1:]))
+        if tc and c1 <= 4 and mlp[0] == 128 and len(mlp) >= 2 and n1 >= 2 * m2:
+            # commuted form (mlp_tc._fp_commuted): the ":interpolate" stage is the m2 known points times W0[:c2] on the tensor cores,
+            # the ":mlp" stage gathers + finishes layer 0 on the CUDA cores and issues only layers 1.. as MMAs
+            costs[s + ":interpolate"] = ("tensor", 2 * B * m2 * up * mlp[0], None, 2 * B * m2 * _r16(up) * mlp[0])
+            costs[s + ":mlp"] = ("tensor", flops, None, 2 * B * n1 * sum(a * b for a, b in zip(mlp, mlp[1:])))
+        else:
+            costs[s + ":interpolate"] = ("hbm", B * (24 * n1 + m2 * up * 4 + n1 * (up + c1) * e_img + n1 * c1 * 4))
+            costs[s + ":mlp"] = ("tensor", flops, None, 2 * B * n1 * sum(_r16(a) * b for a, b in zip(dims, dims[1:])))
         up = mlp[-1]
     return costs
 
@@ -502,9 +516,11 @@ def main():
             ach, peak, unit = amount / (t_ms * 1e-3) / 1e12, peaks["bf16_tflops_sustained"], "TFLOP/s"
         k = {"ms": round(t_ms, 4), "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit, "frac": round(ach / peak, 5),
              "algorithmic": amount, "traffic": ncu_traffic.get(name, {}).get("traffic_bytes")}
-        if bound == "tensor" and tensor_mul != 1:
-            k["tensor_pipe_frac"] = round(tensor_mul * ach / peak, 5)  # bf16x3 issues three bf16 MMAs per algorithmic product
-        if len(costs[name]) > 2:  # search stage: pair evaluations of the scan it replaces, against the measured FP32 rate
+        if bound == "tensor" and len(costs[name]) > 3:
+            # tensor-pipe occupancy: the bf16 MMA flops actually issued (x3 in split-bf16 arithmetic) over the sustained bf16 peak
+            k["issued_flops"] = tensor_mul * costs[name][3]
+            k["tensor_pipe_frac"] = round(tensor_mul * costs[name][3] / (t_ms * 1e-3) / 1e12 / peak, 5)
+        if len(costs[name]) > 2 and costs[name][2] is not None:  # search stage: pair evaluations of the scan it replaces, against the measured FP32 rate
             pe = costs[name][2]
             k["pair_evals"] = pe
             k["fp32"] = {"achieved": round(pe * PAIR_FLOPS / (t_ms * 1e-3) / 1e12, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",

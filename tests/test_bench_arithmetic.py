@@ -43,6 +43,10 @@ def test_search_and_gather_bytes():
     x3 = b.stage_costs(8, "bf16x3")
     assert x3["layer2:ballquery_group"][1] - bf["layer2:ballquery_group"][1] == 8 * 512 * 32 * 128 * 2
     assert x3["layer1:mlp"] == bf["layer1:mlp"]
+    # issued MMA flops per bf16 pass: 16-column k-slices (SA1: 6 -> 16 input columns); the commuted fa_layer4 issues layers 1.. only
+    assert bf["layer1:mlp"][3] == 2 * 8 * m * k * (16 * 32 + 32 * 32 + 32 * 64)
+    assert bf["fa_layer4:mlp"][3] == 2 * 8 * n * (128 * 128 + 128 * 128) and bf["fa_layer4:interpolate"][0] == "tensor"
+    assert b.stage_costs(8, "fp32")["fa_layer4:interpolate"][0] == "hbm"
 
 
 def test_peaks_loader_prefers_measured_file(tmp_path, monkeypatch):

@@ -10,7 +10,7 @@ xyz, col = scenes.scannet_like_batch(0, 2, 4608)
 x, c = torch.from_numpy(xyz).to(dev), torch.from_numpy(col).to(dev)
 specs = backbone.scaled_sa_specs(4608)
 store, _ = backbone.random_variables(dev, sa_specs=specs)
-for prec in ("bf16", "fp32"):
+for prec in ("bf16x3", "bf16", "fp32"):
     out = backbone.forward(x, c, store, sa_specs=specs, precision=prec, l0_half=torch.float16)
 torch.cuda.synchronize()
 fps = gspn_b200.farthest_point_sample(16, x)
