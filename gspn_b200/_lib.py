@@ -66,6 +66,7 @@ SIGNATURES = {
     "gspn_mlp_chain_fp": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P, P, c_int, c_int, P]),
     "gspn_mlp_chain_set_profile": (None, [P]),
     "gspn_mlp_chain_tune": (None, [c_int, c_int, c_int]),
+    "gspn_mlp_chain_tune_fp": (None, [c_int]),
     "gspn_col_moments_f32": (c_int, [c_long, c_int, P, P, P, P]),
     "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),
     "gspn_maxpool_argmax_f32": (c_int, [c_long, c_int, c_int, P, P, P, P]),

@@ -293,6 +293,8 @@ int gspn_group_rows_grad(int b, int n, int c, int m, int nsample, int ld, const 
  * tma_out 0 = row-per-lane 256-bit output stores instead of TMA tensor stores.  Defaults (2, 2, 1) are the measured best. */
 void gspn_mlp_chain_set_profile(long long *prof);
 void gspn_mlp_chain_tune(int occ_cap, int bufs_cap, int tma_out);
+/* gather warps of gspn_mlp_chain_fp: 8 (default; 448 threads, fastest alone) or 4 (320 threads: leaves registers for an FPS CTA on the SM) */
+void gspn_mlp_chain_tune_fp(int gather_warps);
 
 /* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of
  * points2 (b,m,c2) with idx/weight (b,n,3), concatenated with points1 (b,n,c1) (may be NULL, c1=0),

@@ -67,6 +67,45 @@ def test_glue_entry_points_validate_without_a_gpu():
     assert L.gspn_grid_query_workspace_bytes(0, 70000, 5000) == 0
 
 
+def test_round2_entry_points_validate_without_a_gpu():
+    """The chain's arithmetic / image dtypes, the fused multi-radius query, the deterministic backward and the SyncBN split:
+    argument checks come before any CUDA call; the library reads no environment variables."""
+    import ctypes
+    L = _lib.lib()
+    assert L.gspn_mlp_weight_image_bytes(64, 32, _lib.GSPN_MLP_BF16) == 32 * 128
+    assert L.gspn_mlp_weight_image_bytes(64, 32, _lib.GSPN_MLP_BF16X3) == 2 * 32 * 128   # [hi rows | lo rows]
+    assert L.gspn_mlp_weight_image_bytes(64, 32, 7) == 0
+    assert L.gspn_grouped_bytes(256, 6, _lib.GSPN_DT_BF16X2) == 2 * 2 * 16384               # every block a [hi | lo] pair
+    dims = (ctypes.c_int * 2)(64, 32)
+    one = (ctypes.c_void_p * 1)(None)
+    rel = (ctypes.c_int * 1)(1)
+    c = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    # unknown arithmetic -> bad dtype; rows == 0 -> nothing to do; missing image -> null pointer
+    assert L.gspn_mlp_chain(128, 1, c(dims), 0, None, c(one), c(one), c(one), c(rel), 1, None, None, _lib.GSPN_DT_BF16, 9, None) in (
+        _lib.GSPN_E_NULL_PTR, _lib.GSPN_E_BAD_DTYPE)
+    assert L.gspn_mlp_chain(0, 1, c(dims), 0, None, c(one), c(one), c(one), c(rel), 1, None, None, _lib.GSPN_DT_BF16, _lib.GSPN_MLP_BF16X3, None) == 0
+    assert L.gspn_fp_assemble(1, 8, 4, 3, 5, None, None, None, None, None, 64, 9, None) == _lib.GSPN_E_BAD_DTYPE
+    assert L.gspn_fp_assemble(1, 8, 4, 0, 0, None, None, None, None, None, 64, _lib.GSPN_DT_BF16X2, None) == _lib.GSPN_E_BAD_SHAPE
+    rad = (ctypes.c_float * 5)(0.5, 1.0, 1.5, 2.0, 3.0)
+    ns = (ctypes.c_int * 5)(8, 8, 8, 8, 8)
+    ptrs = (ctypes.c_void_p * 5)(*([None] * 5))
+    assert L.gspn_query_ball_point_multi(1, 8, 4, 5, c(rad), c(ns), None, None, c(ptrs), c(ptrs), None) == _lib.GSPN_E_BAD_SHAPE  # > 4 balls
+    assert L.gspn_query_ball_point_multi(1, 8, 4, 2, c(rad), c(ns), None, None, c(ptrs), c(ptrs), None) == _lib.GSPN_E_NULL_PTR
+    assert L.gspn_query_ball_point_multi(0, 8, 4, 2, c(rad), c(ns), None, None, c(ptrs), c(ptrs), None) == 0
+    assert L.gspn_scatter_det_workspace_bytes(2, 100, 16) == 256 + 8 * 2 * 100 * 16
+    assert L.gspn_group_point_grad_det(1, 8, 4, 2, 2, None, None, None, None, 0, None) == _lib.GSPN_E_NULL_PTR
+    assert L.gspn_bn_bwd_apply_f32(8, 4, 4, 1, 1, None, None, None, None, None, None, None, None, None, None, None) == _lib.GSPN_E_BAD_SHAPE  # total < rows
+    assert L.gspn_farthest_point_sample_workspace_bytes(8, 32768, 2048) == 0   # the bucket-pruned kernel is opt-in
+    L.gspn_fps_tune(1)
+    try:
+        assert L.gspn_farthest_point_sample_workspace_bytes(8, 32768, 2048) == 8 * 32768 * 16
+        assert L.gspn_farthest_point_sample_workspace_bytes(8, 8192, 2048) == 0
+    finally:
+        L.gspn_fps_tune(0)
+    for path in ("mlp_tc.cu", "fps.cu", "fps_bucket.cu", "ballquery_group.cu", "grid_search.cu", "gather_ops.cu", "nn_search.cu"):
+        assert "getenv" not in open(os.path.join(ROOT, "gspn_b200", "csrc", path)).read(), path
+
+
 def test_ops_refuse_cpu_tensors():
     import pytest
     import torch
