@@ -458,7 +458,7 @@ def main():
     warm(eng_h, host_in, out_host, n=2 * args.depth)
     e2e_ms = timed_steps(eng_h, host_in, out_host)
     extras = {}
-    if not args.no_extras and tc:
+    if not args.no_extras and tc and world == 1:
         out32 = pinned(torch.float32)
         warm(eng, host_in, out32, n=2 * args.depth)
         e32 = timed_steps(eng, host_in, out32)
