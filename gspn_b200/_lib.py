@@ -76,6 +76,12 @@ SIGNATURES = {
     "gspn_mlp_wgrad_f32": (c_int, [c_long, c_int, c_int, P, c_int, P, P, P, P]),
     "gspn_group_rows_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_fp_assemble": (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, c_int, P]),
+    "gspn_p2p_mailbox_bytes": (c_size_t, [c_int, c_int]),
+    "gspn_p2p_mailbox_create": (c_int, [c_int, c_int, P, P]),
+    "gspn_p2p_mailbox_open": (c_int, [P, P]),
+    "gspn_p2p_mailbox_close": (c_int, [P]),
+    "gspn_p2p_mailbox_destroy": (c_int, [P]),
+    "gspn_p2p_allreduce_f64": (c_int, [c_int, c_int, c_int, P, c_int, P, P]),
     "gspn_nearest_point": (c_int, [c_int, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
     "gspn_box_shrink": (c_int, [c_int, c_int, c_int, P, P, P, P]),
 }

@@ -22,6 +22,7 @@ from ._lib import check
 BN_EPS = 1e-3
 SYNC_BN = True      # whole-batch statistics across ranks (only acts when torch.distributed has > 1 rank)
 SYNC_GROUP = None   # process group of the data-parallel replicas (None = the default group)
+PEER_GROUP = None   # a gspn_b200.p2p.PeerGroup: the moment all-reduces go through NVLink peer memory instead of NCCL (use_peer_moments)
 EQUAL_SHARDS = True # every rank feeds the same number of rows per layer (batch sharding of equal scenes): the global row count is
                     # rows * world and needs no communication -- and no host synchronisation inside the step
 
@@ -29,6 +30,13 @@ EQUAL_SHARDS = True # every rank feeds the same number of rows per layer (batch 
 def _world():
     import torch.distributed as dist
     return dist.get_world_size(SYNC_GROUP) if (SYNC_BN and dist.is_available() and dist.is_initialized()) else 1
+
+
+def use_peer_moments(group):
+    """Route the batch-norm moment all-reduces through a p2p.PeerGroup (one small NVLink kernel per collective, no NCCL, no host
+    synchronisation); None switches back to torch.distributed.  Needs EQUAL_SHARDS (the row count is not communicated)."""
+    global PEER_GROUP
+    PEER_GROUP = group
 
 
 def allreduce_moments(s1, s2, rows, buf=None):
@@ -43,7 +51,10 @@ def allreduce_moments(s1, s2, rows, buf=None):
     if EQUAL_SHARDS:
         if buf is None:
             buf = torch.cat([s1.double(), s2.double()])
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=SYNC_GROUP)
+        if PEER_GROUP is not None and buf.is_cuda:
+            PEER_GROUP.allreduce_(buf)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=SYNC_GROUP)
         return buf[:c], buf[c:2 * c], rows * world
     buf = torch.cat([s1.double(), s2.double(), torch.tensor([float(rows)], dtype=torch.float64, device=s1.device)])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=SYNC_GROUP)

@@ -303,6 +303,20 @@ void gspn_mlp_chain_tune_fp(int gather_warps);
 int gspn_fp_assemble(int b, int n, int m, int c1, int c2, const float *points1, const float *points2,
                      const int *idx, const float *weight, void *a_img, int ld, int image_dtype, gspn_stream_t stream);
 
+/* ---- peer-memory all-reduce of small vectors over NVLink (csrc/p2p.cu): the whole-batch batch-norm statistics of the data-parallel
+ * training form, 52 dependent collectives of a few hundred bytes per step.  Every rank owns a mailbox (created here -- the only entry
+ * points of the library that allocate -- and mapped into the peers through its 64-byte CUDA IPC handle); one small kernel writes the
+ * rank's vector into every peer's mailbox, publishes an epoch flag, waits for all contributions to its own mailbox and sums them in
+ * rank order (bit-identical, deterministic sums on every rank).  No NCCL call, no host synchronisation, CUDA-graph capturable.
+ *   mailboxes: HOST array of `world` device pointers, mailboxes[r] = rank r's mailbox as mapped in this process ([rank] = its own);
+ *   data (device, `count` <= max_doubles doubles) is reduced in place; every rank must issue the same sequence of calls. */
+size_t gspn_p2p_mailbox_bytes(int world, int max_doubles);
+int gspn_p2p_mailbox_create(int world, int max_doubles, void **mailbox, unsigned char *ipc_handle64);
+int gspn_p2p_mailbox_open(const unsigned char *ipc_handle64, void **peer_mailbox);
+int gspn_p2p_mailbox_close(void *peer_mailbox);
+int gspn_p2p_mailbox_destroy(void *mailbox);
+int gspn_p2p_allreduce_f64(int rank, int world, int max_doubles, void *const *mailboxes, int count, double *data, gspn_stream_t stream);
+
 /* ---- brute-force nearest-neighbour glue around the path ------------------------------
  * One-directional 1-NN: for every query (b,n,3) the nearest reference point (b,m,3): squared distance dist (b,n)
  * and index idx (b,n), lowest index on ties.  Replaces the model's dense (B,N,M) distance tensors + argmin:

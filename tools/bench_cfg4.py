@@ -27,12 +27,18 @@ ap.add_argument("--steps", type=int, default=6)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--precision", default=None)
 ap.add_argument("--gpus", type=int, default=1)
+ap.add_argument("--nccl-moments", action="store_true", help="A/B: batch-norm moment all-reduces through NCCL instead of NVLink peer memory")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+peer = None
+if world > 1 and not args.nccl_moments:
+    from gspn_b200 import p2p
+    peer = p2p.PeerGroup(dev)
+    train.use_peer_moments(peer)
 B, N, NSMP, NPTS = 2, 18000, 256, 512
 store, _ = backbone.random_variables(dev)  # same seed on every rank -> identical initial parameters
 offset = torch.zeros(3, device=dev, requires_grad=True)
@@ -88,7 +94,9 @@ if rank == 0:
         "value": world * B / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (training form: CUDA-core GEMMs)", "data": "synthetic",
         "config": {"workload": "config4: data-parallel train step, 2 scenes x 18000 pts per GPU, 256 proposals/scene, NCCL all-reduce of "
-                               "gradients + whole-batch batch-norm statistics", "sync_bn": bool(train.SYNC_BN), "params": int(sum(p.numel() for p in params))},
+                               "gradients + whole-batch batch-norm statistics", "sync_bn": bool(train.SYNC_BN), "moment_allreduce": "NVLink peer memory (csrc/p2p.cu)" if peer is not None else ("NCCL" if world > 1 else "none"), "params": int(sum(p.numel() for p in params))},
         "loss": float(loss), "parameters_identical_across_ranks": same}))
+if peer is not None:
+    peer.close()
 if world > 1:
     dist.destroy_process_group()
