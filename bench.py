@@ -344,13 +344,14 @@ def main():
     ap.add_argument("--fp-warps", type=int, default=0, help="A/B door: gather warps of the feature-propagation chain (4 or 8)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 = BASELINE.json's headline (default); cfg3 / cfg4 = tools/bench_cfg3.py / tools/bench_cfg4.py under the same launch")
-    args = ap.parse_args()
+    args, passthrough = ap.parse_known_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
     if args.workload != "cfg2":
-        import runpy
-        sys.argv = [sys.argv[0], "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--precision", args.precision] if args.precision else [])
+        import runpy  # flags bench.py does not know (e.g. --nccl-moments) go to the workload's own parser
+        sys.argv = ([sys.argv[0], "--steps", str(args.steps), "--warmup", str(args.warmup), "--gpus", str(args.gpus)] +
+                    (["--precision", args.precision] if args.precision else []) + passthrough)
         runpy.run_path(os.path.join(ROOT, "tools", "bench_%s.py" % args.workload), run_name="__main__")
         return 0
 
@@ -359,6 +360,8 @@ def main():
     from gspn_b200 import _lib, backbone, scenes
     from gspn_b200 import pointnet_util as pu
 
+    if passthrough:
+        raise SystemExit("bench.py: unknown arguments %r" % (passthrough,))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: gspn_b200 has no CPU path (use --impl reference for the CPU arm)")
     L = _lib.lib()  # fail loudly if the extension is missing

@@ -95,7 +95,7 @@ if rank == 0:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (training form: CUDA-core GEMMs)", "data": "synthetic",
         "config": {"workload": "config4: data-parallel train step, 2 scenes x 18000 pts per GPU, 256 proposals/scene, NCCL all-reduce of "
                                "gradients + whole-batch batch-norm statistics", "sync_bn": bool(train.SYNC_BN), "moment_allreduce": "NVLink peer memory (csrc/p2p.cu)" if peer is not None else ("NCCL" if world > 1 else "none"), "params": int(sum(p.numel() for p in params))},
-        "loss": float(loss), "parameters_identical_across_ranks": same}))
+        "loss": float(loss.detach()), "parameters_identical_across_ranks": same}))
 if peer is not None:
     peer.close()
 if world > 1:
