@@ -341,6 +341,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--fps-mapping", default=None, help="A/B door: threads,ppt,cluster of the FPS kernel for 32768-point clouds")
     ap.add_argument("--fps-buckets", action="store_true", help="A/B door: the bucket-pruned single-CTA FPS kernel")
+    ap.add_argument("--fps-pruned", action="store_true", help="A/B door: the bucket-pruned cluster FPS kernel")
+    ap.add_argument("--dynamic-tiles", action="store_true", help="A/B door: chain kernels take their tiles by work stealing (cluster launch control)")
     ap.add_argument("--fp-warps", type=int, default=0, help="A/B door: gather warps of the feature-propagation chain (4 or 8)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 = BASELINE.json's headline (default); cfg3 / cfg4 = tools/bench_cfg3.py / tools/bench_cfg4.py under the same launch")
@@ -369,8 +371,12 @@ def main():
         L.gspn_fps_tune_mapping(*[int(v) for v in args.fps_mapping.split(",")])
     if args.fps_buckets:
         L.gspn_fps_tune(1)
+    if args.fps_pruned:
+        L.gspn_fps_tune(2)
     if args.fp_warps:
         L.gspn_mlp_chain_tune_fp(args.fp_warps)
+    if args.dynamic_tiles:
+        L.gspn_mlp_chain_tune_sched(1)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -36,6 +36,7 @@ SIGNATURES = {
     "gspn_fps_tune": (None, [c_int]),
     "gspn_fps_tune_mapping": (None, [c_int, c_int, c_int]),
     "gspn_fps_bucket_profile": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P, P]),
+    "gspn_fps_pruned_profile": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P, P]),
     "gspn_fps_profile": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P]),
     "gspn_gather_point": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
     "gspn_gather_point_grad": (c_int, [c_int, c_int, c_int, c_int, P, P, P, P]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     "gspn_mlp_chain_set_profile": (None, [P]),
     "gspn_mlp_chain_tune": (None, [c_int, c_int, c_int]),
     "gspn_mlp_chain_tune_fp": (None, [c_int]),
+    "gspn_mlp_chain_tune_sched": (None, [c_int]),
     "gspn_col_moments_f32": (c_int, [c_long, c_int, P, P, P, P]),
     "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),
     "gspn_maxpool_argmax_f32": (c_int, [c_long, c_int, c_int, P, P, P, P]),

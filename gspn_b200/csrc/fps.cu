@@ -18,103 +18,13 @@
 // its winner among equal maxima is the lowest (k mod 512, k) -- thread-strided scan with strict '>'
 // (:130,:146) + left-wins tree (:158).  The key  ((k&511)<<23)|(k>>9)  orders exactly like that,
 // independent of how points are mapped to threads here.
-#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
-#include "common.cuh"
+#include "fps_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace gspn {
-
-__device__ __forceinline__ unsigned fps_key(int k) { return ((unsigned)(k & 511) << 23) | ((unsigned)k >> 9); }
-__device__ __forceinline__ int fps_unkey(unsigned key) { return (int)(((key & 0x7FFFFFu) << 9) | (key >> 23)); }
-
-struct Cand {  // a candidate: squared distance bits, tie-break key, coordinates
-    int dbits;
-    unsigned key;
-    float x, y, z;
-};
-
-// warp-wide (max dist, then min key); every lane returns the winner's fields.
-__device__ __forceinline__ Cand warp_argmax(Cand c) {
-    int wm = __reduce_max_sync(GSPN_FULL_MASK, c.dbits);  // non-negative floats order as ints; -1.0f (empty) is negative
-    unsigned kk = (c.dbits == wm) ? c.key : 0xFFFFFFFFu;
-    unsigned wk = __reduce_min_sync(GSPN_FULL_MASK, kk);
-    int src = __ffs(__ballot_sync(GSPN_FULL_MASK, kk == wk)) - 1;
-    Cand r;
-    r.dbits = wm;
-    r.key = wk;
-    r.x = __shfl_sync(GSPN_FULL_MASK, c.x, src);
-    r.y = __shfl_sync(GSPN_FULL_MASK, c.y, src);
-    r.z = __shfl_sync(GSPN_FULL_MASK, c.z, src);
-    return r;
-}
-
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t f_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// shared::cta address -> shared::cluster address of the same variable in CTA `rank`
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-// asynchronous DSMEM stores that signal the destination CTA's mbarrier (complete_tx): no cluster barrier,
-// no gpu-scope fence on the round's critical path
-__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(a),
-                 "r"(b), "r"(c), "r"(d), "r"(rbar)
-                 : "memory");
-}
-__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t a, uint32_t rbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a), "r"(rbar) : "memory");
-}
-__device__ __forceinline__ void f_mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void f_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void f_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "FW_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra FD_%=;\n\t"
-        "bra FW_%=;\n\t"
-        "FD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-
-// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two points per instruction, each half IEEE round-to-nearest,
-// so the per-point result is bit-identical to sqdist_fma
-__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
-constexpr int kMaxWarps = 32;
-constexpr int kMaxCand = 128;  // CLUSTER * warps-per-CTA candidates per round in the all-to-all exchange
-
-struct __align__(16) Slot { float x, y, z; int dbits; };
 
 // argmax over a thread's PPT updated distances as a tournament (depth log2 PPT instead of a PPT-long
 // dependent chain); the left operand survives ties, so the lowest j -- the lowest key -- wins.
@@ -502,7 +412,12 @@ size_t gspn_fps_bucket_workspace_bytes(int b, int n);
 int gspn_fps_bucket_launch(int b, int n, int m, const float *inp, int *out, void *workspace, long long *prof, cudaStream_t s);
 // Opt-in (gspn_fps_tune(1)): exact and 80x fewer distance evaluations, but measured SLOWER per cloud than the full-scan cluster kernel
 // (2.4 ms vs 1.04 ms at 32768 -> 2048): off by default.
-static int g_fps_buckets = 0;
+// fps_pruned.cu (gspn_fps_tune(2)): the same pruning on the 8-CTA cluster (points and distances stay in registers, statically indexed).
+// Also exact, also slower than the full scan (1.5 ms): a round's critical path is the one warp whose buckets the sample touches.
+size_t gspn_fps_pruned_workspace_bytes(int b, int n);
+int gspn_fps_pruned_launch(int b, int n, int m, const float *inp, int *out, void *workspace, long long *prof, cudaStream_t s);
+static int g_fps_mode = 0;  // gspn_fps_tune: 0 = full-scan kernels (default), 1 = single-CTA bucket kernel, 2 = pruned cluster kernel
+#define g_fps_buckets (g_fps_mode == 1)
 static int g_fps_big[3] = {0, 0, 0};  // tuning door (gspn_fps_tune_mapping): (threads, ppt, cluster) for clouds above 16384 points
 
 // Tuning door: per-phase cycle counts of thread 0 (compute+tournament, warp reduce, exchange, table reduce),
@@ -530,11 +445,13 @@ extern "C" size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m
     if (b <= 0) return 0;
     if (g_fps_buckets)
         if (const size_t wb = gspn_fps_bucket_workspace_bytes(b, n)) return wb;  // the sorted copy of the bucket-pruned kernel
+    if (g_fps_mode == 2)
+        if (const size_t wb = gspn_fps_pruned_workspace_bytes(b, n)) return wb;  // the curve-ordered copy
     if (n <= kMaxClusterStream) return 0;
     return sizeof(float) * (size_t)b * (size_t)n;
 }
 
-extern "C" void gspn_fps_tune(int use_buckets) { g_fps_buckets = use_buckets != 0; }
+extern "C" void gspn_fps_tune(int mode) { g_fps_mode = (mode == 1 || mode == 2) ? mode : 0; }
 extern "C" void gspn_fps_tune_mapping(int threads, int ppt, int cluster) { g_fps_big[0] = threads; g_fps_big[1] = ppt; g_fps_big[2] = cluster; }
 
 extern "C" int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
@@ -545,6 +462,16 @@ extern "C" int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, in
     if (need == 0) return GSPN_E_UNSUPPORTED;
     if (workspace == nullptr || workspace_bytes < need) return GSPN_E_WORKSPACE;
     return gspn_fps_bucket_launch(b, n, m, inp, out, workspace, prof3, as_stream(stream));
+}
+
+extern "C" int gspn_fps_pruned_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
+                                       long long *prof5, gspn_stream_t stream) {
+    GSPN_REQUIRE(b > 0 && n > 0 && m > 0);
+    GSPN_REQUIRE_PTR(inp); GSPN_REQUIRE_PTR(out); GSPN_REQUIRE_PTR(prof5);
+    const size_t need = gspn_fps_pruned_workspace_bytes(b, n);
+    if (need == 0) return GSPN_E_UNSUPPORTED;
+    if (workspace == nullptr || workspace_bytes < need) return GSPN_E_WORKSPACE;
+    return gspn_fps_pruned_launch(b, n, m, inp, out, workspace, prof5, as_stream(stream));
 }
 
 extern "C" int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *out, int threads, int ppt, int cluster,
@@ -571,6 +498,10 @@ extern "C" int gspn_farthest_point_sample(int b, int n, int m, const float *inp,
     if (g_fps_buckets && workspace != nullptr) {
         const size_t need = gspn_fps_bucket_workspace_bytes(b, n);
         if (need && workspace_bytes >= need) return gspn_fps_bucket_launch(b, n, m, inp, out, workspace, nullptr, as_stream(stream));
+    }
+    if (g_fps_mode == 2 && workspace != nullptr) {
+        const size_t need = gspn_fps_pruned_workspace_bytes(b, n);
+        if (need && workspace_bytes >= need) return gspn_fps_pruned_launch(b, n, m, inp, out, workspace, nullptr, as_stream(stream));
     }
     if (n <= kMaxResident) return gspn_farthest_point_sample_cfg(b, n, m, inp, out, 0, 0, 0, stream);
     if (n <= kMaxClusterStream && b <= 65535) {

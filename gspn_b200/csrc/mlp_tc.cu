@@ -71,6 +71,7 @@ struct ChainParams {
     uint32_t stage_off, stg_bytes, stg_h_off;  // per-epilogue-warp output staging boxes (TMA output path)
     uint32_t affine_off;
     int tma_out;
+    int dyn_tiles;    // 1: the grid has one CTA per tile and running CTAs take over not-yet-launched ones (walk_next); 0: static stride
     long long *prof;  // optional: per-phase cycle counters of CTA 0 (tools/tc_profile.py)
     // kModeGatherSA: layer 0's operand rows [features(c) | xyz - centre - shift | 0] (c+3 <= 8) built from the ball-query indices
     const int *g_idx;      // (b, m, nsample)
@@ -123,6 +124,57 @@ __device__ __forceinline__ void mb_wait_relaxed(uint32_t bar, uint32_t parity) {
         __nanosleep(100);
     }
 }
+// ---- which tile next.  Static (the default): tile += gridDim.x of a grid sized to the SMs.  Dynamic (gspn_mlp_chain_tune_sched(1)): the
+// grid has one CTA per tile, and a CTA that finishes a tile cancels a CTA the hardware has not launched yet and does that CTA's tile
+// instead (clusterlaunchcontrol.try_cancel, the work-stealing form of a persistent kernel; tools/probes/clc_probe.cu: every tile
+// exactly once, ~760 cycles per query).  Built for the pipelined step, where FPS clusters hold part of the GPU for a millisecond and
+// a static grid's CTAs that found no SM run as a second wave; measured there it is a wash (0.735 vs 0.722 ms/step: the step is bound
+// by register-file occupancy, not by wave quantisation) and 7 us slower on the 256-tile chains, so it stays a door.
+// One lane (operand-producer warp 0) sends the queries, one in flight beyond the last answer read; every warp of the CTA walks
+// the same answers through a ring of kSched (full, empty) mbarrier pairs.  A query is only sent after a successful one.
+constexpr int kSched = 8;
+struct __align__(16) SchedRing {
+    uint4 resp[kSched];      // the 16-byte answers
+    uint64_t full[kSched];   // answer landed (complete_tx)
+    uint64_t empty[kSched];  // every warp of the CTA has read it
+};
+__device__ __forceinline__ void walk_issue(uint32_t ring, int k) {
+    const int s = k & (kSched - 1), u = k / kSched;
+    const uint32_t full = ring + (uint32_t)offsetof(SchedRing, full) + 8 * s, empty = ring + (uint32_t)offsetof(SchedRing, empty) + 8 * s;
+    if (u >= 1) mb_wait_relaxed(empty, (uint32_t)((u - 1) & 1));  // every warp has read the slot's previous answer
+    mb_expect_tx(full, 16);
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(ring + 16 * s), "r"(full)
+                 : "memory");
+}
+// The tile after `tile`, or -1.  WARP: called by all 32 lanes (one arrival per warp); otherwise by a single thread.  q: the caller's
+// count of answers read so far.  issuer: this thread sends the queries.
+template <bool WARP>
+__device__ __forceinline__ int walk_next(const ChainParams &p, uint32_t ring, int &q, int tile, int lane, bool issuer) {
+    if (!p.dyn_tiles) {
+        tile += gridDim.x;
+        return tile < (int)p.ntiles ? tile : -1;
+    }
+    const int s = q & (kSched - 1), u = q / kSched;
+    mb_wait(ring + (uint32_t)offsetof(SchedRing, full) + 8 * s, (uint32_t)(u & 1));
+    uint32_t valid, x;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+        "selp.u32 %1, 1, 0, p1;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+        : "=r"(x), "=r"(valid)
+        : "r"(ring + 16 * s)
+        : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot is rewritten through the async proxy
+    if (WARP) __syncwarp();
+    if (!WARP || lane == 0) mb_arrive(ring + (uint32_t)offsetof(SchedRing, empty) + 8 * s);
+    ++q;
+    if (issuer && valid) walk_issue(ring, q);
+    return valid ? (int)x : -1;
+}
+
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                  "r"(bar)
@@ -387,6 +439,7 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 4];
+    __shared__ SchedRing sched;
 
     // warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the
     // MMA issuer's operands can live in uniform registers (no per-instruction R2UR waterfall)
@@ -407,6 +460,10 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
             mb_init(s_u32(&bars[i]), (i >= 2 * kMaxStages && i < 3 * kMaxStages) ? NPW : 1);
         mb_init(epi_done, p.epi_warps);  // one elected lane per epilogue warp arrives once per step
         mb_init(epi_done + 8, p.epi_warps);
+        for (int i = 0; i < kSched; ++i) {
+            mb_init(s_u32(&sched.full[i]), 1);
+            mb_init(s_u32(&sched.empty[i]), EPI + NPW + 2);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // folded bias/BN affine of every layer -> smem ([scale_l | shift_l] per layer)
@@ -439,22 +496,24 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
     const int last_l = p.nlayers - 1;
     const int npass_last = (p.N[last_l] + p.dcols - 1) / p.dcols;
     const int kb0 = p.KB[0];
-    const long my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const uint32_t ring = s_u32(&sched);
+    int wq = 0;  // answers of the tile ring this warp has read
 
     if (warp >= EPI && warp < EPI + NPW) {
         // ================= operand producers: keep the layer-0 ring full for the whole kernel, independent of the MMA/epilogue
         // timeline, so the operand of the next tile is in flight while the epilogue warps are busy
         if (p.mode == kModeBulk) {
             if (warp == EPI && lane == 0) {
-                int s = 0, par = 0, kb = 0;
-                long t = blockIdx.x;
-                const long total_a = my_tiles * kb0;
-                for (long i = 0; i < total_a; ++i) {
-                    if (i >= p.a_stages) mb_wait_relaxed(a_empty + 8 * s, (uint32_t)(par ^ 1));
-                    mb_expect_tx(a_full + 8 * s, p.a_stage_bytes);
-                    bulk_load(aring + s * p.a_stage_bytes, p.a + ((size_t)t * kb0 + kb) * p.a_stage_bytes, p.a_stage_bytes, a_full + 8 * s);
-                    if (++kb == kb0) { kb = 0; t += gridDim.x; }
-                    if (++s == p.a_stages) { s = 0; par ^= 1; }
+                int s = 0, par = 0;
+                long i = 0;
+                if (p.dyn_tiles) walk_issue(ring, 0);
+                for (int t = blockIdx.x; t >= 0; t = walk_next<false>(p, ring, wq, t, 0, true)) {
+                    for (int kb = 0; kb < kb0; ++kb, ++i) {
+                        if (i >= p.a_stages) mb_wait_relaxed(a_empty + 8 * s, (uint32_t)(par ^ 1));
+                        mb_expect_tx(a_full + 8 * s, p.a_stage_bytes);
+                        bulk_load(aring + s * p.a_stage_bytes, p.a + ((size_t)t * kb0 + kb) * p.a_stage_bytes, p.a_stage_bytes, a_full + 8 * s);
+                        if (++s == p.a_stages) { s = 0; par ^= 1; }
+                    }
                 }
             }
         } else if (NPW == 2 && p.mode == kModeGatherSA) {
@@ -464,23 +523,26 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
             const int pw = warp - EPI;
             const int c = p.g_c;
             int s = 0, par = 0;
-            long t = blockIdx.x;
+            int t = blockIdx.x;
+            const bool sender = pw == 0 && lane == 0;
             int ii[2], nxt[2];
-            auto load_idx = [&](long tile, int (&dst)[2]) {
+            auto load_idx = [&](int tile, int (&dst)[2]) {
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const long row = tile * kTileRows + pw * 64 + rr * 32 + lane;
-                    dst[rr] = (tile < p.ntiles && row < p.rows) ? __ldg(p.g_idx + row) : -1;
+                    const long row = (long)tile * kTileRows + pw * 64 + rr * 32 + lane;
+                    dst[rr] = (tile >= 0 && tile < p.ntiles && row < p.rows) ? __ldg(p.g_idx + row) : -1;
                 }
             };
+            if (sender && p.dyn_tiles) walk_issue(ring, 0);
+            int tn = walk_next<true>(p, ring, wq, t, lane, sender);  // one tile ahead: its indices are requested while this one is built
             load_idx(t, nxt);
-            for (long i = 0; i < my_tiles; ++i, t += gridDim.x) {
+            for (long i = 0; t >= 0; ++i) {
                 ii[0] = nxt[0]; ii[1] = nxt[1];
-                load_idx(t + gridDim.x, nxt);
+                load_idx(tn, nxt);
                 float gx[2][3], cx[2][3], sh[2][3], f[2][5];
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const long row = t * kTileRows + pw * 64 + rr * 32 + lane;
+                    const long row = (long)t * kTileRows + pw * 64 + rr * 32 + lane;
                     const bool ok = ii[rr] >= 0;
                     const uint32_t q = ok ? p.g_div_k.div((uint32_t)row) : 0u;  // global query index cloud*m + j
                     const uint32_t cloud = p.g_div_m.div(q);
@@ -524,6 +586,8 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
                 __syncwarp();
                 if (lane == 0) mb_arrive(a_full + 8 * s);
                 if (++s == p.a_stages) { s = 0; par ^= 1; }
+                t = tn;
+                if (t >= 0) tn = walk_next<true>(p, ring, wq, t, lane, sender);
             }
         } else if ((NPW == 8 || NPW == 4) && p.mode == kModeFP) {
             // the feature-propagation module's first layer on the CUDA cores, from the pre-multiplied coarse features:
@@ -541,8 +605,10 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
             for (int a = 0; a < 4; ++a)
                 wb[a] = a < c1 ? __ldg(reinterpret_cast<const float4 *>(p.f_w0b + (size_t)a * n0 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
             int s = 0, par = 0;  // s: first of the tile's two stages (a_stages is even in this mode)
-            long t = blockIdx.x;
-            for (long i = 0; i < my_tiles; ++i, t += gridDim.x) {
+            long i = 0;
+            const bool sender = pw == 0 && lane == 0;
+            if (sender && p.dyn_tiles) walk_issue(ring, 0);
+            for (int t = blockIdx.x; t >= 0; t = walk_next<true>(p, ring, wq, t, lane, sender), ++i) {
                 if (2 * i >= p.a_stages) {
                     mb_wait_relaxed(a_empty + 8 * s, (uint32_t)(par ^ 1));
                     mb_wait_relaxed(a_empty + 8 * (s + 1), (uint32_t)(par ^ 1));
@@ -554,7 +620,7 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int r = st0 + u * NPW;
-                        const long grow = t * kTileRows + r;
+                        const long grow = (long)t * kTileRows + r;
                         const bool ok = grow < p.rows;
                         const long gr = ok ? grow : 0;
                         const uint32_t cloud = p.f_div_n.div((uint32_t)gr);
@@ -609,7 +675,7 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
         if (lane == 0) {
             int s = 0, par = 0;
             long cnt = 0;
-            for (long i = 0; i < my_tiles; ++i) {
+            for (int t = blockIdx.x; t >= 0; t = walk_next<false>(p, ring, wq, t, 0, false)) {
                 for (int l = 0; l < p.nlayers; ++l) {
                     const int Nl = p.N[l];
                     const int npass = (l == last_l) ? npass_last : 1;
@@ -658,7 +724,7 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
         const uint32_t b_lo_off = ((uint32_t)p.nch * 128u) >> 4;   // lo weight rows inside a stage
         const uint32_t a_lo_blk = (uint32_t)kTileBytes >> 4;        // lo operand block inside a layer-0 stage
         const uint32_t ta_hi = tmem + (uint32_t)p.a_col, ta_lo = ta_hi + (uint32_t)p.a_lo_off;
-        for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile >= 0; tile = walk_next<true>(p, ring, wq, tile, lane, false)) {
             for (int l = 0; l < p.nlayers; ++l) {
                 const int Nl = p.N[l], KBl = p.KB[l], NSl = p.NS[l];
                 const int npass = (l == last_l) ? npass_last : 1;
@@ -743,7 +809,7 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
         long estep = 0;  // steps alternate between the TMEM accumulator buffers exactly as the issuer's do
         const int quad = warp & 3, half = warp >> 2, nhalf = EPI >> 2;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-        for (long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile >= 0; tile = walk_next<true>(p, ring, wq, tile, lane, false)) {
             int ao = 0;  // running offset of layer l's [scale | shift] in the affine table
             for (int l = 0; l < p.nlayers; ++l) {
                 const int Nl = p.N[l];
@@ -765,7 +831,7 @@ __global__ void __launch_bounds__((EPI + NPW + 2) * 32, MINB)
                     ec.sc = sc; ec.sh = sh; ec.stg = sm + p.stage_off + warp * p.stg_bytes;
                     ec.ta_hi = tmem + lane_base + (uint32_t)p.a_col;
                     ec.Nl = Nl; ec.col0 = ps * p.dcols; ec.lane = lane;
-                    ec.grow = tile * kTileRows + quad * 32 + lane; ec.row0 = tile * kTileRows + quad * 32;
+                    ec.grow = (long)tile * kTileRows + quad * 32 + lane; ec.row0 = (long)tile * kTileRows + quad * 32;
                     ec.last = last; ec.relu = p.relu[l] != 0;
                     epi_columns<SPLIT>(p, &tm_f32, &tm_h, ec, tmem + lane_base + buf * p.dcols, c_lo, c_hi);
                     if (p.prof) pt3 = clock64();
@@ -941,7 +1007,7 @@ static bool encode_out_map(CUtensorMap *tm, void *base, long rows, int n, int ki
 }
 
 // ---- tuning doors (benchmark A/B runs only): process-wide, set explicitly through the ABI -- nothing is read from the environment
-static struct ChainTune { int occ_cap, bufs_cap, tma_out, fp_warps; long long *prof; } g_tune = {2, 2, 1, 8, nullptr};
+static struct ChainTune { int occ_cap, bufs_cap, tma_out, fp_warps, dyn_tiles; long long *prof; } g_tune = {2, 2, 1, 8, 0, nullptr};
 extern "C" void gspn_mlp_chain_set_profile(long long *prof) { g_tune.prof = prof; }
 extern "C" void gspn_mlp_chain_tune(int occ_cap, int bufs_cap, int tma_out) {
     g_tune.occ_cap = (occ_cap == 1) ? 1 : 2;
@@ -949,6 +1015,7 @@ extern "C" void gspn_mlp_chain_tune(int occ_cap, int bufs_cap, int tma_out) {
     g_tune.tma_out = tma_out != 0;
 }
 extern "C" void gspn_mlp_chain_tune_fp(int gather_warps) { g_tune.fp_warps = gather_warps == 4 ? 4 : 8; }
+extern "C" void gspn_mlp_chain_tune_sched(int dynamic_tiles) { g_tune.dyn_tiles = dynamic_tiles != 0; }
 
 // per-device facts the launcher needs (SM count; the opt-in shared-memory attribute is per device too)
 struct DevInfo { int sms; };
@@ -1090,8 +1157,11 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     // never let more CTAs co-reside than TMEM can serve: inflate the request if shared memory alone would allow it
     const size_t min_smem = (size_t)(228 * 1024) / (occ + 1) - 1024 + 1;
     if (smem < min_smem) smem = min_smem;
+    // dynamic tiles: one CTA per tile; the ones the hardware has not launched yet are taken over by running CTAs (walk_next)
+    p.dyn_tiles = g_tune.dyn_tiles;
     long grid = (long)di->sms * occ;
-    if (grid > p.ntiles) grid = p.ntiles;
+    if (grid > p.ntiles || p.dyn_tiles) grid = p.ntiles;
+    if (grid > 0x7FFFFFFFL) return GSPN_E_UNSUPPORTED;
     int dev = 0;
     GSPN_CUDA_OK(cudaGetDevice(&dev));
     cudaError_t e = cudaErrorInvalidValue;

@@ -70,10 +70,11 @@ int gspn_fp32_peak_probe(int blocks, int iters, float *scratch, double *flops_ou
  * (out[:,0]=0; ties -> lowest (k mod 512, k)).  The reference's temp (32,n) scratch is not needed.  Kernels by cloud size:
  *   up to 131072 points (gspn_fps_max_resident_points()): register-resident cluster kernels (csrc/fps.cu), no workspace; up to
  *   524288 a 16-CTA cluster keeps the distances in registers and streams coordinates from L2; above that the single-CTA fallback
- *   needs workspace.  Opt-in, after gspn_fps_tune(1), for 8193 .. 32768 points with workspace: the exact bucket-pruned single-CTA
- *   kernel (csrc/fps_bucket.cu: the cloud sorted into spatial buckets, resident in shared memory + tensor memory + registers of ONE
- *   SM; a round only updates the buckets the new sample can reach -- same indices, 80x fewer distance evaluations, one SM instead
- *   of eight, but measured slower per cloud, so it is not the default).
+ *   needs workspace.  Opt-in for 8193 .. 32768 points with workspace, two exact bucket-PRUNED kernels (the cloud sorted along a
+ *   Hilbert curve into 1024 buckets of 32 points; a round only updates the buckets whose bounding box the new sample can reach --
+ *   same indices, 80x fewer distance evaluations): gspn_fps_tune(1) = csrc/fps_bucket.cu, resident in shared memory + tensor memory
+ *   + registers of ONE SM; gspn_fps_tune(2) = csrc/fps_pruned.cu, register-resident on the 8-CTA cluster.  Both measured slower
+ *   per cloud than the full scan (the round's dependent chain, not the arithmetic, is what binds), so neither is the default.
  * Pass workspace of gspn_farthest_point_sample_workspace_bytes(b,n,m) bytes (0 when none is used). */
 size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m);
 int gspn_fps_max_resident_points(void);
@@ -84,16 +85,22 @@ int gspn_farthest_point_sample(int b, int n, int m, const float *inp, int *out,
 int gspn_farthest_point_sample_cfg(int b, int n, int m, const float *inp, int *out,
                                    int threads, int ppt, int cluster, gspn_stream_t stream);
 
-/* Tuning doors (process-wide, not thread-safe).  gspn_fps_tune(1) switches the bucket-pruned kernel on (default 0: full-scan
- * kernels for every size).  gspn_fps_bucket_profile runs the bucket kernel and writes for cloud 0: prof3[0] = SM cycles of the round loop,
+/* Tuning doors (process-wide, not thread-safe).  gspn_fps_tune(mode): 0 = full-scan kernels for every size (default), 1 = the
+ * single-CTA bucket kernel where it applies, 2 = the pruned cluster kernel where it applies.  gspn_fps_bucket_profile runs the bucket kernel and writes for cloud 0: prof3[0] = SM cycles of the round loop,
  * prof3[1] = rounds, prof3[2] = bucket updates, prof3[3..7] = warp 0's cycles in: box tests, bucket updates, warp argmax, barrier
  * wait, table reduce, prof3[8] = bucket updates that needed the full argmax (prof3: 12 x int64, zeroed by the caller). */
-void gspn_fps_tune(int use_buckets);
+void gspn_fps_tune(int mode);
 /* (threads per CTA, points per thread, CTAs per cluster) of the register-resident kernel for clouds above 16384 points; 0,0,0 = the
  * built-in table.  Same results for every legal choice. */
 void gspn_fps_tune_mapping(int threads, int ppt, int cluster);
 int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
                             long long *prof3, gspn_stream_t stream);
+
+/* Runs the pruned cluster kernel (curve sort + rounds) and writes for cloud 0: prof5[0] = thread 0's cycles in box test + bucket
+ * updates + warp candidate, prof5[2] = candidate exchange, prof5[3] = table reduce, prof5[4] = bucket updates over all warps
+ * (prof5: 8 x int64, zeroed by the caller). */
+int gspn_fps_pruned_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
+                            long long *prof5, gspn_stream_t stream);
 
 /* Tuning door: per-phase SM-cycle counts of thread 0 of cloud 0, summed over the m-1 rounds:
  * prof4[0..3] = distance update + argmax, warp reduce, candidate exchange, table reduce. */
@@ -295,6 +302,11 @@ void gspn_mlp_chain_set_profile(long long *prof);
 void gspn_mlp_chain_tune(int occ_cap, int bufs_cap, int tma_out);
 /* gather warps of gspn_mlp_chain_fp: 8 (default; 448 threads, fastest alone) or 4 (320 threads: leaves registers for an FPS CTA on the SM) */
 void gspn_mlp_chain_tune_fp(int gather_warps);
+/* tile scheduling of the chain kernels: 0 (default) = a grid sized to the SMs walking the 128-row tiles with a static stride;
+ * 1 = one CTA per tile in the grid, and a CTA that finishes a tile takes over a CTA the hardware has not launched yet
+ * (clusterlaunchcontrol.try_cancel): whatever SMs are free share the tiles as they come.  Same results either way; measured a wash
+ * in the pipelined step, so it is a door. */
+void gspn_mlp_chain_tune_sched(int dynamic_tiles);
 
 /* Feature-propagation front end (utils/pointnet_util.py:156-165) fused: three_interpolate of
  * points2 (b,m,c2) with idx/weight (b,n,3), concatenated with points1 (b,n,c1) (may be NULL, c1=0),

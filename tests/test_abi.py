@@ -95,14 +95,17 @@ def test_round2_entry_points_validate_without_a_gpu():
     assert L.gspn_scatter_det_workspace_bytes(2, 100, 16) == 256 + 8 * 2 * 100 * 16
     assert L.gspn_group_point_grad_det(1, 8, 4, 2, 2, None, None, None, None, 0, None) == _lib.GSPN_E_NULL_PTR
     assert L.gspn_bn_bwd_apply_f32(8, 4, 4, 1, 1, None, None, None, None, None, None, None, None, None, None, None) == _lib.GSPN_E_BAD_SHAPE  # total < rows
-    assert L.gspn_farthest_point_sample_workspace_bytes(8, 32768, 2048) == 0   # the bucket-pruned kernel is opt-in
-    L.gspn_fps_tune(1)
+    # the curve-ordered copy of the pruned FPS kernels: both opt-in, none for the full scan
+    assert L.gspn_farthest_point_sample_workspace_bytes(8, 32768, 2048) == 0
+    assert L.gspn_fps_pruned_profile(1, 8192, 300, None, None, None, 0, None, None) == _lib.GSPN_E_NULL_PTR
     try:
-        assert L.gspn_farthest_point_sample_workspace_bytes(8, 32768, 2048) == 8 * 32768 * 16
-        assert L.gspn_farthest_point_sample_workspace_bytes(8, 8192, 2048) == 0
+        for mode in (1, 2):
+            L.gspn_fps_tune(mode)
+            assert L.gspn_farthest_point_sample_workspace_bytes(8, 32768, 2048) == 8 * 32768 * 16
+            assert L.gspn_farthest_point_sample_workspace_bytes(8, 8192, 2048) == 0
     finally:
         L.gspn_fps_tune(0)
-    for path in ("mlp_tc.cu", "fps.cu", "fps_bucket.cu", "ballquery_group.cu", "grid_search.cu", "gather_ops.cu", "nn_search.cu"):
+    for path in ("mlp_tc.cu", "fps.cu", "fps_bucket.cu", "fps_pruned.cu", "ballquery_group.cu", "grid_search.cu", "gather_ops.cu", "nn_search.cu"):
         assert "getenv" not in open(os.path.join(ROOT, "gspn_b200", "csrc", path)).read(), path
 
 

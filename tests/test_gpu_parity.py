@@ -104,17 +104,20 @@ FPS_BUCKET_CASES = [
 ]
 
 
+@pytest.mark.parametrize("mode", [2, 1], ids=["pruned_cluster", "bucket_single_cta"])
 @pytest.mark.parametrize("name,make,m", FPS_BUCKET_CASES, ids=[c[0] for c in FPS_BUCKET_CASES])
-def test_fps_bucket_pruned_kernel_bit_exact(cuda, oracle, name, make, m):
-    """8193 .. 32768 points: the bucket-pruned single-CTA kernel (csrc/fps_bucket.cu) against the oracle, the reference's own kernel
-    and this library's full-scan cluster kernel -- duplicates, degenerate boxes, coordinates of either sign, ragged last bucket."""
+def test_fps_bucket_pruned_kernel_bit_exact(cuda, oracle, name, make, m, mode):
+    """8193 .. 32768 points: the opt-in bucket-pruned kernels -- the cluster form (csrc/fps_pruned.cu) and the single-CTA form
+    (csrc/fps_bucket.cu) -- against the oracle, the reference's own kernel and this library's full-scan cluster kernel: duplicates,
+    degenerate boxes, coordinates of either sign, ragged last bucket."""
     xyz = make()
     x = T(xyz, cuda)
     L = _lib.lib()
-    scan = N(gspn_b200.farthest_point_sample(m, x))  # default: the full-scan cluster kernel
-    L.gspn_fps_tune(1)                               # opt in to the bucket-pruned kernel
     try:
-        assert L.gspn_farthest_point_sample_workspace_bytes(xyz.shape[0], xyz.shape[1], m) > 0  # the bucket path is the one taken
+        assert L.gspn_farthest_point_sample_workspace_bytes(xyz.shape[0], xyz.shape[1], m) == 0
+        scan = N(gspn_b200.farthest_point_sample(m, x))  # default: the full-scan cluster kernel
+        L.gspn_fps_tune(mode)
+        assert L.gspn_farthest_point_sample_workspace_bytes(xyz.shape[0], xyz.shape[1], m) > 0  # the pruned path is the one taken
         got = N(gspn_b200.farthest_point_sample(m, x))
     finally:
         L.gspn_fps_tune(0)
@@ -122,6 +125,23 @@ def test_fps_bucket_pruned_kernel_bit_exact(cuda, oracle, name, make, m):
     if refgpu.available():
         assert np.array_equal(got, N(refgpu.fps(m, x)))
     assert np.array_equal(got, scan)
+
+
+def test_fps_pruned_cluster_kernel_on_config2_counts_its_work(cuda):
+    """8 x 32768 -> 2048 on the pruned cluster kernel == the default full scan; its profile door reports the bucket updates it made
+    (full scan: 2047 x 1024 per cloud)."""
+    xyz = scenes.scannet_like_batch(0, 8, 32768)[0]
+    x = T(xyz, cuda)
+    L = _lib.lib()
+    wsb = 8 * 32768 * 16
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=cuda)
+    out = torch.empty((8, 2048), dtype=torch.int32, device=cuda)
+    prof = torch.zeros(8, dtype=torch.int64, device=cuda)
+    _lib.check(L.gspn_fps_pruned_profile(8, 32768, 2048, x.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb, prof.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "fps_pruned_profile")
+    assert np.array_equal(N(out), N(gspn_b200.farthest_point_sample(2048, x)))
+    updates = int(prof[4])
+    assert 1024 <= updates < 2047 * 1024 // 20, updates
 
 
 @pytest.mark.parametrize("n,m", [(131072 + 1000, 40), (300000, 64), (524288 + 7, 24)])
@@ -1006,6 +1026,27 @@ def test_gather_in_chain_equals_tile_image_path(cuda, precision):
         finally:
             mlp_tc.GATHER_IN_CHAIN = True
         assert torch.equal(a[2], b_[2]) and torch.equal(a[1], b_[1])
+
+
+def test_chain_dynamic_tiles_bit_identical(cuda):
+    """gspn_mlp_chain_tune_sched(1): the chain kernels take their tiles by work stealing (cluster launch control) instead of a static
+    stride.  Which CTA runs which tile must not show: a whole backbone forward (tile-image, in-chain gather and commuted
+    feature-propagation chains, several thousand tiles on the first and last level) is bit-identical, twice over."""
+    from gspn_b200 import backbone
+    xyz, col = scenes.scannet_like_batch(130, 4, 32768)
+    x, c = T(xyz, cuda), T(col, cuda)
+    store, _ = backbone.random_variables(cuda)
+    L = _lib.lib()
+    ref = backbone.forward(x, c, store, l0_half=torch.float16)
+    L.gspn_mlp_chain_tune_sched(1)
+    try:
+        for _ in range(2):
+            got = backbone.forward(x, c, store, l0_half=torch.float16)
+            assert torch.equal(got["l0_points"], ref["l0_points"]) and torch.equal(got["l0_points_half"], ref["l0_points_half"])
+            for a, b_ in zip(got["points"][1:], ref["points"][1:]):
+                assert torch.equal(a, b_)
+    finally:
+        L.gspn_mlp_chain_tune_sched(0)
 
 
 def test_module_inputs_are_validated_not_reinterpreted(cuda):

@@ -31,5 +31,21 @@ gspn_b200.nearest_point(x, x[:, :200].contiguous())
 gspn_b200.box_shrink(torch.rand(2, 16, 6, device=dev), x)
 big = torch.rand(1, 140000, 3, device=dev)
 gspn_b200.farthest_point_sample(8, big)
+# round-2 kernels: one scan for nested balls, order-independent backward, training form, bucket-pruned FPS (opt-in), single-rank mailbox
+from gspn_b200 import ops, train, _lib
+gspn_b200.ops.query_ball_point_multi([0.3, 0.6, 1.2], [8, 16, 32], x[:, :2000].contiguous(), x[:, :64].contiguous())
+ops.DETERMINISTIC_BACKWARD = True
+gspn_b200.group_point(p, idx).sum().backward()
+gspn_b200.three_interpolate(p, i3, w).sum().backward()
+gspn_b200.gather_point(p, fps % 300).sum().backward()
+ops.DETERMINISTIC_BACKWARD = False
+leaves = train.trainable(store)
+out = backbone.forward(x, c, store, sa_specs=specs, is_training=True, bn_decay=0.9)
+out["l0_points"].square().mean().backward()
+for mode in (1, 2):
+    _lib.lib().gspn_fps_tune(mode)
+    big2 = torch.rand(2, 9000, 3, device=dev)
+    gspn_b200.farthest_point_sample(300, big2)
+_lib.lib().gspn_fps_tune(0)
 torch.cuda.synchronize()
 print("sanitize workload done")
