@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--depth", type=int, default=12, help="batches kept in flight (CUDA-graph lanes on separate streams)")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--fps-mapping", default=None, help="A/B door: threads,ppt,cluster of the FPS kernel for 32768-point clouds")
+    ap.add_argument("--fps-pack", type=int, default=0, help="A/B door: clouds per FPS CTA (1 or 2)")
     ap.add_argument("--fps-buckets", action="store_true", help="A/B door: the bucket-pruned single-CTA FPS kernel")
     ap.add_argument("--fps-pruned", action="store_true", help="A/B door: the bucket-pruned cluster FPS kernel")
     ap.add_argument("--dynamic-tiles", action="store_true", help="A/B door: chain kernels take their tiles by work stealing (cluster launch control)")
@@ -369,6 +370,8 @@ def main():
     L = _lib.lib()  # fail loudly if the extension is missing
     if args.fps_mapping:
         L.gspn_fps_tune_mapping(*[int(v) for v in args.fps_mapping.split(",")])
+    if args.fps_pack:
+        L.gspn_fps_tune_pack(args.fps_pack)
     if args.fps_buckets:
         L.gspn_fps_tune(1)
     if args.fps_pruned:

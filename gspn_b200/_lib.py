@@ -35,6 +35,7 @@ SIGNATURES = {
     "gspn_farthest_point_sample_cfg": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P]),
     "gspn_fps_tune": (None, [c_int]),
     "gspn_fps_tune_mapping": (None, [c_int, c_int, c_int]),
+    "gspn_fps_tune_pack": (None, [c_int]),
     "gspn_fps_bucket_profile": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P, P]),
     "gspn_fps_pruned_profile": (c_int, [c_int, c_int, c_int, P, P, P, c_size_t, P, P]),
     "gspn_fps_profile": (c_int, [c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P]),

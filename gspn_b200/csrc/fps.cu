@@ -51,24 +51,38 @@ struct Tourney {
 // Requires (blockDim.x*CLUSTER) % 512 == 0 or PPT == 1 so that a thread's points have ascending keys,
 // and CLUSTER * (blockDim.x/32) <= kMaxCand when CLUSTER > 1.
 // dynamic smem: float4 xyz copy, [PPT][blockDim.x], so only the round's winner lane fetches coordinates.
-template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false, int CPL = (CLUSTER > 1 ? 2 : 1)>
+// CPC (clouds per CTA, CLUSTER > 1 only): 2 = the CTA is two independent halves, each doing what a CTA of blockDim.x / 2 threads does
+// for its own cloud (nothing on the round path is CTA-wide: warp collectives and per-half mbarriers only).  Same latency, and the
+// FPS state of a batch sits on half as many SMs, each of them full, instead of a third of the registers of twice as many -- which
+// leaves whole SMs to the big MLP-chain CTAs of the other lanes in the pipelined step.
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE = false, int CPL = (CLUSTER > 1 ? 2 : 1), int CPC = 1>
 __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, const float *__restrict__ xyz, int *__restrict__ out,
-                                                               long long *__restrict__ prof = nullptr) {
+                                                               long long *__restrict__ prof = nullptr, int nclouds = 0) {
+    static_assert(CPC == 1 || CLUSTER > 1, "halves only synchronise through their own mbarriers");
     extern __shared__ float4 sxyz[];
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, acc[4] = {0, 0, 0, 0};
     // candidate table: 32*CPL entries per parity; entries no warp owns stay "empty" (-1, max key) forever,
     // so the per-round reduce is CPL unconditional loads per lane
-    __shared__ Slot wslot[2][32 * CPL];
-    __shared__ unsigned wkey[2][32 * CPL];
-    __shared__ __align__(8) uint64_t xbar[2];
+    __shared__ Slot wslot_[CPC][2][32 * CPL];
+    __shared__ unsigned wkey_[CPC][2][32 * CPL];
+    __shared__ __align__(8) uint64_t xbar_[CPC][2];
 
-    const int cloud = blockIdx.y;
+    const int tpc = blockDim.x / CPC;                             // threads of this cloud's part of the CTA
+    const int part = CPC > 1 ? (int)threadIdx.x / tpc : 0;
+    const int ltid = (int)threadIdx.x - part * tpc;
+    Slot (*wslot)[32 * CPL] = wslot_[part];
+    unsigned (*wkey)[32 * CPL] = wkey_[part];
+    uint64_t *xbar = xbar_[part];
+    int cloud = blockIdx.y * CPC + part;
+    const bool live = CPC == 1 || cloud < nclouds;                // odd batch: the last half redoes the last cloud and writes nothing
+    if (!live) cloud = nclouds - 1;
     unsigned rank = 0;
     if (CLUSTER > 1) rank = cg::this_cluster().block_rank();
-    const int T = blockDim.x * CLUSTER;
-    const int gtid = rank * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int T = tpc * CLUSTER;
+    const int gtid = rank * tpc + ltid;
+    const int lane = ltid & 31, warp = ltid >> 5, nwarps = tpc >> 5;
     const float *p = xyz + (size_t)cloud * n * 3;
+    float4 *sx = sxyz + (size_t)part * PPT * tpc;
 
     constexpr bool PACKED = (PPT % 2 == 0);
     constexpr int NP = PACKED ? PPT / 2 : 1;
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
             px[j] = py[j] = pz[j] = 0.f;
             td[j] = -1.0f;  // min(d,-1) = -1 never beats a real point (distances are >= 0)
         }
-        sxyz[j * blockDim.x + threadIdx.x] = make_float4(px[j], py[j], pz[j], 0.f);  // read back by this thread only
+        sx[j * tpc + ltid] = make_float4(px[j], py[j], pz[j], 0.f);  // read back by this thread only
     }
     if (PACKED) {
 #pragma unroll
@@ -95,17 +109,16 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         }
     }
     float x1 = __ldg(p), y1 = __ldg(p + 1), z1 = __ldg(p + 2);  // old = 0 (:114)
-    if (gtid == 0) out[(size_t)cloud * m] = 0;
+    if (gtid == 0 && live) out[(size_t)cloud * m] = 0;
     const int ncand = CLUSTER * nwarps;
-    for (int i = threadIdx.x; i < 2 * 32 * CPL; i += blockDim.x) {
-        (&wslot[0][0])[i] = Slot{0.f, 0.f, 0.f, __float_as_int(-1.0f)};
-        (&wkey[0][0])[i] = 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < CPC * 2 * 32 * CPL; i += blockDim.x) {
+        (&wslot_[0][0][0])[i] = Slot{0.f, 0.f, 0.f, __float_as_int(-1.0f)};
+        (&wkey_[0][0][0])[i] = 0xFFFFFFFFu;
     }
     __syncthreads();
     if (CLUSTER > 1) {
         if (threadIdx.x == 0) {
-            f_mbar_init(f_smem_u32(&xbar[0]), 1);
-            f_mbar_init(f_smem_u32(&xbar[1]), 1);
+            for (int i = 0; i < CPC * 2; ++i) f_mbar_init(f_smem_u32(&xbar_[0][0] + i), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         cluster_barrier();  // every CTA resident and its mbarriers initialised before any DSMEM traffic
@@ -113,7 +126,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
 
     for (int r = 1; r < m; ++r) {
         const int par = r & 1;
-        if (CLUSTER > 1 && threadIdx.x == 0)  // this round's phase completes after ncand x (16+4) bytes have landed
+        if (CLUSTER > 1 && ltid == 0)  // this round's phase completes after ncand x (16+4) bytes have landed
             f_mbar_expect_tx(f_smem_u32(&xbar[par]), (uint32_t)ncand * 20u);
         if (PROFILE) t0 = clock64();
         if (PACKED) {
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         c.dbits = __float_as_int(best);
         c.key = fps_key(gtid + bj * T);
         // every lane starts fetching its own best point's coordinates; the load overlaps the warp reduce
-        const float4 q = sxyz[bj * blockDim.x + threadIdx.x];
+        const float4 q = sx[bj * tpc + ltid];
         int wm = __reduce_max_sync(GSPN_FULL_MASK, c.dbits);
         unsigned kk = (c.dbits == wm) ? c.key : 0xFFFFFFFFu;
         unsigned wk = __reduce_min_sync(GSPN_FULL_MASK, kk);
@@ -187,14 +200,14 @@ __global__ void __launch_bounds__(MAXT, 1) fps_resident_kernel(int n, int m, con
         }
         c = warp_argmax(w);
         x1 = c.x; y1 = c.y; z1 = c.z;
-        if (gtid == 0) out[(size_t)cloud * m + r] = fps_unkey(c.key);
+        if (gtid == 0 && live) out[(size_t)cloud * m + r] = fps_unkey(c.key);
         if (PROFILE) {
             asm volatile("" ::"f"(x1));
             long long t4 = clock64();
             acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2; acc[3] += t4 - t3;
         }
     }
-    if (PROFILE && gtid == 0 && cloud == 0 && prof) {
+    if (PROFILE && gtid == 0 && cloud == 0 && live && prof) {
         prof[0] = acc[0]; prof[1] = acc[1]; prof[2] = acc[2]; prof[3] = acc[3];
     }
     if (CLUSTER > 1) cluster_barrier();  // no CTA exits while a peer may still address its smem
@@ -324,14 +337,14 @@ __global__ void __launch_bounds__(kBigThreads, 1) fps_cluster_stream_kernel(int 
     cluster_barrier();
 }
 
-template <int PPT, int CLUSTER, int MAXT, bool PROFILE, int CPL>
+template <int PPT, int CLUSTER, int MAXT, bool PROFILE, int CPL, int CPC = 1>
 static int launch_resident_cpl(int b, int n, int m, const float *inp, int *out, int threads, cudaStream_t s, long long *prof) {
-    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT, PROFILE, CPL>;
+    auto kern = fps_resident_kernel<PPT, CLUSTER, MAXT, PROFILE, CPL, CPC>;
     if (CLUSTER > 8) GSPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CLUSTER, b, 1);
-    cfg.blockDim = dim3(threads, 1, 1);
-    const size_t smem = sizeof(float4) * (size_t)PPT * threads;
+    cfg.gridDim = dim3(CLUSTER, (b + CPC - 1) / CPC, 1);
+    cfg.blockDim = dim3(threads * CPC, 1, 1);
+    const size_t smem = sizeof(float4) * (size_t)PPT * threads * CPC;
     if (smem > 48 * 1024) GSPN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -342,7 +355,7 @@ static int launch_resident_cpl(int b, int n, int m, const float *inp, int *out, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out, prof));
+    GSPN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, n, m, inp, out, prof, b));
     return GSPN_OK;
 }
 
@@ -367,7 +380,10 @@ static int dispatch_cluster(int cluster, int b, int n, int m, const float *inp, 
     return GSPN_E_UNSUPPORTED;
 }
 
+static int g_fps_pack = 1;  // gspn_fps_tune_pack: clouds per CTA of the (128, 32, 8) mapping
 static int launch_cfg(int b, int n, int m, const float *inp, int *out, int threads, int ppt, int cluster, cudaStream_t s) {
+    if (g_fps_pack == 2 && threads == 128 && ppt == 32 && cluster == 8 && b >= 2 && b <= 65535 && (long)threads * ppt * cluster >= n)
+        return launch_resident_cpl<32, 8, 256, false, 1, 2>(b, n, m, inp, out, threads, s, nullptr);
     if (threads < 32 || threads > 1024 || threads % 32) return GSPN_E_UNSUPPORTED;
     if (ppt > 1 && (threads * cluster) % 512) return GSPN_E_UNSUPPORTED;  // ascending keys per thread
     if ((long)threads * ppt * cluster < n) return GSPN_E_UNSUPPORTED;
@@ -452,6 +468,7 @@ extern "C" size_t gspn_farthest_point_sample_workspace_bytes(int b, int n, int m
 }
 
 extern "C" void gspn_fps_tune(int mode) { g_fps_mode = (mode == 1 || mode == 2) ? mode : 0; }
+extern "C" void gspn_fps_tune_pack(int clouds_per_cta) { g_fps_pack = clouds_per_cta == 2 ? 2 : 1; }
 extern "C" void gspn_fps_tune_mapping(int threads, int ppt, int cluster) { g_fps_big[0] = threads; g_fps_big[1] = ppt; g_fps_big[2] = cluster; }
 
 extern "C" int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,

@@ -93,6 +93,9 @@ void gspn_fps_tune(int mode);
 /* (threads per CTA, points per thread, CTAs per cluster) of the register-resident kernel for clouds above 16384 points; 0,0,0 = the
  * built-in table.  Same results for every legal choice. */
 void gspn_fps_tune_mapping(int threads, int ppt, int cluster);
+/* clouds per CTA of the 8-CTA cluster kernel for 16385 .. 32768 points: 2 = every 256-thread CTA is two independent 128-thread
+ * halves, one cloud each (same results and latency; a batch's FPS state fills half as many SMs instead of a third of twice as many). */
+void gspn_fps_tune_pack(int clouds_per_cta);
 int gspn_fps_bucket_profile(int b, int n, int m, const float *inp, int *out, void *workspace, size_t workspace_bytes,
                             long long *prof3, gspn_stream_t stream);
 

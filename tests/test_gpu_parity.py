@@ -89,6 +89,23 @@ def test_fps_full_size_config2(cuda, oracle):
     assert all(a >= b * (1 - 1e-6) for a, b in zip(sel, sel[1:]))
 
 
+@pytest.mark.parametrize("b", [8, 5, 2])
+def test_fps_two_clouds_per_cta_same_indices(cuda, oracle, b):
+    """gspn_fps_tune_pack(2): the 8-CTA cluster kernel with two independent 128-thread halves per CTA, one cloud each (odd batch:
+    the last half idles on a copy of the last cloud) -- same indices as one cloud per CTA and as the oracle."""
+    xyz = scenes.with_duplicates(scenes.scannet_like_batch(31, b, 32768 - 5 * b)[0], 0.05)
+    x = T(xyz, cuda)
+    L = _lib.lib()
+    one = N(gspn_b200.farthest_point_sample(700, x))
+    L.gspn_fps_tune_pack(2)
+    try:
+        two = N(gspn_b200.farthest_point_sample(700, x))
+    finally:
+        L.gspn_fps_tune_pack(1)
+    assert np.array_equal(one, two)
+    assert np.array_equal(two[-1:], oracle.farthest_point_sample(700, xyz[-1:]))
+
+
 FPS_BUCKET_CASES = [
     ("scene_16384", lambda: scenes.scannet_like_batch(3, 3, 16384)[0], 700),
     ("n8193_smallest", lambda: scenes.scannet_like_batch(4, 2, 8193)[0], 300),
