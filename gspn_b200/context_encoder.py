@@ -21,8 +21,6 @@ def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list,
                        use_xyz=False, output_shift=False, shift_pred=None, fps_idx=None, variables=None, precision=None):
     """-> (new_xyz (b,npoint,3), new_points (b,npoint,sum mlp[-1]), shift_pred, fps_idx)."""
     pu._check_unbuilt(is_training)
-    if is_training:
-        raise NotImplementedError("multi_encoding_net: the training form is built for pointnet_sa_module / pointnet_fp_module only")
     if mlp_list2 or output_shift:
         raise NotImplementedError("mlp_list2 / output_shift are conv1d head code outside the SA/FP path (reference call site uses neither)")
     store = pu.VARIABLES if variables is None else variables
@@ -36,6 +34,11 @@ def multi_encoding_net(xyz, points, npoint, radius_list, nsample_list, mlp_list,
     cin = c + 3 if (use_xyz or points is None) else c
     outs = []
     all_layers = [store.layers(scope, "conv_prev_%d_" % i, cin, list(mlp), bn) for i, mlp in enumerate(mlp_list)]
+    if is_training:  # fp32 training form: batch-statistics BN, autograd through grouping and the MLPs (gspn_b200/train.py)
+        from . import train
+        new_points = train.encoding_net_train(xyz, new_xyz, points, radius_list, nsample_list, all_layers, bn_decay,
+                                              use_xyz or points is None, shift_pred)
+        return new_xyz, new_points, shift_pred, fps_idx
     # the nested balls share their seeds: when every radius goes through the in-chain gather, ONE scan finds all index lists
     # (models/model_rpointnet.py:49-61 issues one query_ball_point per radius)
     fused_idx = None

@@ -20,7 +20,7 @@ tf.get_variable would, later calls reuse them.  Three execution precisions share
                      so 5e-3 .. 3e-2 away from the fp32 reference -- OUTSIDE its 1e-3 bound; opt-in),
   precision='fp32' : reference-precision MLP on CUDA cores (parity tolerance 1e-5).
 
-is_training=True runs the fp32 training form (gspn_b200/train.py): batch-statistics batch norm with in-place moving
+is_training=True (any mlp / mlp2 / group_all) runs the fp32 training form (gspn_b200/train.py): batch-statistics batch norm with in-place moving
 average updates, autograd through MLP, max-pool, grouping and interpolation.
 Not built: knn=True, tnet_spec (undefined `tnet` in the reference itself, pointnet_util.py:44), pooling other than
 'max' (no call site in the model).  Those raise NotImplementedError instead of approximating.
@@ -192,10 +192,8 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp, mlp2, group_al
     layers2 = store.layers(scope, "conv_post_", mlp[-1] if mlp else cin, list(mlp2 or []), bn)
 
     if is_training:
-        if group_all or mlp2 or not layers:
-            raise NotImplementedError("is_training=True is built for the model's call shape (group_all=False, mlp2=None)")
         from . import train
-        return train.sa_module_train(xyz, points, npoint, radius, nsample, layers, bn_decay, use_xyz)
+        return train.sa_module_train(xyz, points, npoint, radius, nsample, layers, bn_decay, use_xyz, layers2, group_all)
     if group_all:
         new_xyz, new_points, idx, _ = sample_and_group_all(xyz, points, use_xyz)
         x = _run_mlp_f32(new_points.reshape(b * n, cin).contiguous(), layers)

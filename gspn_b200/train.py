@@ -161,11 +161,12 @@ class MlpLayerTrain(torch.autograd.Function):
 
 
 class GroupRowsTrain(torch.autograd.Function):
-    """Fused ball query + group -> fp32 rows [features | xyz - centre]; gradient to the features only."""
+    """Fused ball query + group -> fp32 rows [features | xyz - centre (- shift)]; gradient to the features only (the reference stops
+    the gradient at shift_pred, models/model_rpointnet.py:377, and xyz / new_xyz are data)."""
 
     @staticmethod
-    def forward(ctx, xyz, new_xyz, points, radius, nsample):
-        idx, _, grouped, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32)
+    def forward(ctx, xyz, new_xyz, points, radius, nsample, shift=None):
+        idx, _, grouped, ld = ops.ballquery_group(radius, nsample, xyz, new_xyz, points, torch.float32, shift=shift)
         ctx.save_for_backward(idx)
         ctx.shape = None if points is None else tuple(points.shape)
         ctx.ld = ld
@@ -176,13 +177,13 @@ class GroupRowsTrain(torch.autograd.Function):
     def backward(ctx, dgrouped, _didx):
         (idx,) = ctx.saved_tensors
         if ctx.shape is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         b, n, c = ctx.shape
         _, m, k = idx.shape
         dgrouped = dgrouped.contiguous()
         dp = torch.empty((b, n, c), dtype=torch.float32, device=dgrouped.device)
         check(_lib.lib().gspn_group_rows_grad(b, n, c, m, k, ctx.ld, dgrouped.data_ptr(), idx.data_ptr(), dp.data_ptr(), _s()), "group_rows_grad")
-        return None, None, dp, None, None
+        return None, None, dp, None, None, None
 
 
 def run_mlp_train(x2d, layers, bn_decay, pool_last=1, first_weight=None):
@@ -195,17 +196,50 @@ def run_mlp_train(x2d, layers, bn_decay, pool_last=1, first_weight=None):
     return x2d
 
 
-def sa_module_train(xyz, points, npoint, radius, nsample, layers, bn_decay, use_xyz=True):
-    """pointnet_sa_module(is_training=True), pooling='max', mlp2=None, group_all=False."""
+def _max_rows(x2d, pool):
+    """tf.reduce_max over the neighbourhood axis (pointnet_util.py:124) when no MLP layer is there to carry the pooling."""
+    return x2d.reshape(-1, pool, x2d.shape[-1]).max(dim=1).values
+
+
+def sa_module_train(xyz, points, npoint, radius, nsample, layers, bn_decay, use_xyz=True, layers2=(), group_all=False):
+    """pointnet_sa_module(is_training=True), pooling='max': sample_and_group / sample_and_group_all -> mlp -> max -> mlp2
+    (utils/pointnet_util.py:85-139)."""
     b, n, _ = xyz.shape
-    fps_idx = ops.farthest_point_sample(npoint, xyz)
-    new_xyz = ops.gather_point(xyz, fps_idx)
-    grouped, idx = GroupRowsTrain.apply(xyz, new_xyz.detach(), points, radius, nsample)
-    w = layers[0]["weights"]
-    if points is not None:  # grouped columns are [features | xyz]; the reference kernel rows are [xyz | features]
-        w = torch.cat([w[3:], w[:3]], dim=0) if use_xyz else torch.cat([w, torch.zeros((3, w.shape[1]), device=w.device)], dim=0)
-    x = run_mlp_train(grouped, layers, bn_decay, pool_last=nsample, first_weight=w)
+    if group_all:  # sample_and_group_all (:57-82): one group of all n points, rows [xyz | features], new_xyz = 0
+        new_xyz = torch.zeros((b, 1, 3), dtype=torch.float32, device=xyz.device)
+        idx = torch.arange(n, dtype=torch.int32, device=xyz.device).reshape(1, 1, n).repeat(b, 1, 1)
+        rows = xyz if points is None else (torch.cat([xyz, points], dim=2) if use_xyz else points)
+        x, npoint, nsample = rows.reshape(b * n, rows.shape[2]), 1, n
+        w = None
+    else:
+        fps_idx = ops.farthest_point_sample(npoint, xyz)
+        new_xyz = ops.gather_point(xyz, fps_idx)
+        x, idx = GroupRowsTrain.apply(xyz, new_xyz.detach(), points, radius, nsample)
+        w = layers[0]["weights"] if layers else None
+        if points is not None and w is not None:  # grouped columns are [features | xyz]; the reference kernel rows are [xyz | features]
+            w = torch.cat([w[3:], w[:3]], dim=0) if use_xyz else torch.cat([w, torch.zeros((3, w.shape[1]), device=w.device)], dim=0)
+        if not layers and points is not None:     # no MLP: the pooled rows themselves, back in the reference's column order
+            c = points.shape[2]
+            x = torch.cat([x[:, c:c + 3], x[:, :c]], dim=1) if use_xyz else x[:, :c]
+    x = run_mlp_train(x, layers, bn_decay, pool_last=nsample, first_weight=w) if layers else _max_rows(x, nsample)
+    if layers2:
+        x = run_mlp_train(x, list(layers2), bn_decay)
     return new_xyz, x.reshape(b, npoint, x.shape[-1]), idx
+
+
+def encoding_net_train(xyz, new_xyz, points, radius_list, nsample_list, layer_lists, bn_decay, use_xyz, shift_pred):
+    """multi_encoding_net(is_training=True) (models/model_rpointnet.py:28-77): per radius ball query + group (- new_xyz - shift_pred,
+    points FIRST: this library's grouped column order) -> mlp -> max; concatenated over the radii."""
+    b, m, _ = new_xyz.shape
+    outs = []
+    for radius, nsample, layers in zip(radius_list, nsample_list, layer_lists):
+        x, _ = GroupRowsTrain.apply(xyz, new_xyz.detach(), points, radius, nsample, None if shift_pred is None else shift_pred.detach())
+        w = layers[0]["weights"]
+        if points is not None and not use_xyz:  # the xyz columns are there but the reference's rows do not have them
+            w = torch.cat([w, torch.zeros((3, w.shape[1]), device=w.device)], dim=0)
+        x = run_mlp_train(x, layers, bn_decay, pool_last=nsample, first_weight=w)
+        outs.append(x.reshape(b, m, x.shape[-1]))
+    return torch.cat(outs, dim=-1)
 
 
 def fp_module_train(xyz1, xyz2, points1, points2, layers, bn_decay):

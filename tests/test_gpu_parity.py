@@ -575,7 +575,7 @@ def test_pointnet_fp_module_fp32_matches_oracle(cuda, oracle, mlp, with_p1):
 def test_unbuilt_variants_raise(cuda):
     x = torch.zeros(1, 64, 3, device=cuda)
     with pytest.raises(NotImplementedError):
-        gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], [8], False, True, None, "t1")  # training form with mlp2
+        gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], None, False, False, None, "t1", knn=True)
     with pytest.raises(NotImplementedError):
         gspn_b200.pointnet_sa_module(x, None, 8, 0.5, 4, [8], None, False, False, None, "t2", pooling="avg")
 
@@ -991,6 +991,97 @@ def test_sa_module_training_forward_backward(cuda, oracle):
     _, out_inf, _ = gspn_b200.pointnet_sa_module(T(xyz, cuda), T(feats, cuda), m, r, k, [32, 32, 64], None, False, False, None, "sa", variables=st,
                                                  precision="fp32")
     assert out_inf.shape == out.shape
+
+
+def test_sa_module_training_mlp2_and_group_all(cuda, oracle):
+    """is_training=True beyond the model's call shape (VERDICT r1 missing 8): mlp2 after the pooling (utils/pointnet_util.py:132-139),
+    group_all (:104-106, sample_and_group_all :57-82) and mlp=[] -- against the PyTorch fp32 restatement on the oracle's grouping."""
+    rng = np.random.RandomState(3)
+    xyz, _ = scenes.scannet_like_batch(102, 2, 1024)
+    feats = rng.randn(2, 1024, 5).astype(np.float32)
+    m, r, k = 64, 0.4, 16
+    x_t = T(xyz, cuda)
+    for case in ("mlp2", "group_all", "no_mlp"):
+        mlp = [] if case == "no_mlp" else [16, 32]
+        mlp2 = [24] if case != "group_all" else [8, 8]
+        l1 = rand_layers(rng, 8, mlp) if mlp else []
+        l2 = rand_layers(rng, mlp[-1] if mlp else 8, mlp2)
+        mine1, mine2, ref1, ref2 = clone_layers(l1, cuda), clone_layers(l2, cuda), clone_layers(l1, cuda), clone_layers(l2, cuda)
+        st = pu.VariableStore(device=cuda)
+        st["s/conv"], st["s/conv_post_"] = mine1, mine2
+        f, fr = T(feats, cuda).requires_grad_(True), T(feats, cuda).requires_grad_(True)
+        ga = case == "group_all"
+        nx, out, idx = gspn_b200.pointnet_sa_module(x_t, f, m, r, k, mlp, mlp2, ga, True, 0.9, "s", variables=st)
+        if ga:
+            assert tuple(out.shape) == (2, 1, mlp2[-1]) and tuple(idx.shape) == (2, 1, 1024) and float(nx.abs().max()) == 0.0
+            x = torch.cat([x_t, fr], dim=2).reshape(-1, 8)
+            pool, groups = 1024, 1
+        else:
+            enx, _, eidx, _ = oracle.sample_and_group(m, r, k, xyz, feats)
+            assert np.array_equal(N(idx), eidx)
+            ii = T(eidx.astype(np.int64), cuda)
+            gx = torch.stack([x_t[b][ii[b]] for b in range(2)]) - T(enx, cuda).unsqueeze(2)
+            gp = torch.stack([fr[b][ii[b]] for b in range(2)])
+            x = torch.cat([gx, gp], dim=-1).reshape(-1, 8)
+            pool, groups = k, m
+        h = torch_mlp_train(x, ref1, 0.9, pool) if mlp else x.reshape(-1, pool, 8).max(dim=1).values
+        want = torch_mlp_train(h, ref2, 0.9, 1).reshape(2, groups, mlp2[-1])
+        gout = T(rng.randn(*out.shape).astype(np.float32), cuda)
+        out.backward(gout)
+        want.backward(gout)
+        np.testing.assert_allclose(N(out), N(want), err_msg=case, **TRAIN_TOL)
+        np.testing.assert_allclose(N(f.grad), N(fr.grad), err_msg=case, **TRAIN_TOL)
+        for a, b_ in zip(mine1 + mine2, ref1 + ref2):
+            for key in ("weights", "biases", "gamma", "beta"):
+                np.testing.assert_allclose(N(a[key].grad), N(b_[key].grad), rtol=2e-3, atol=5e-4, err_msg=case + "/" + key)
+            # (moving_variance is not compared: torch's running_var takes the unbiased variance, tf.nn.moments / this library the biased one)
+            np.testing.assert_allclose(N(a["moving_mean"]), N(b_["moving_mean"]), rtol=1e-4, atol=1e-5)
+
+
+def test_multi_encoding_net_training_forward_backward(cuda, oracle):
+    """multi_encoding_net(is_training=True) (models/model_rpointnet.py:28-77; the context encoder is trained in config 4): three
+    nested balls, rows [points | xyz - seed - shift_pred], batch-statistics BN, max, concat -- against the PyTorch fp32 restatement on
+    the oracle's ball-query indices; gradients reach the point features and every parameter, not shift_pred (stop_gradient, :377)."""
+    from gspn_b200 import context_encoder
+    rng = np.random.RandomState(5)
+    xyz, col = scenes.scannet_like_batch(103, 2, 2048)
+    x_t = T(xyz, cuda)
+    radii, ks, mlps = [0.3, 0.6, 0.9], [16, 16, 32], [[16, 32]] * 3
+    fps = gspn_b200.farthest_point_sample(32, x_t)
+    shift_np = (rng.randn(2, 32, 3) * 0.05).astype(np.float32)
+    shift = T(shift_np, cuda).requires_grad_(True)
+    lnp = [rand_layers(rng, 6, m_) for m_ in mlps]
+    mine, ref = [clone_layers(l, cuda) for l in lnp], [clone_layers(l, cuda) for l in lnp]
+    st = pu.VariableStore(device=cuda)
+    for i in range(3):
+        st["ctx/conv_prev_%d_" % i] = mine[i]
+    f, fr = T(col, cuda).requires_grad_(True), T(col, cuda).requires_grad_(True)
+    nx, out, sp, _ = context_encoder.multi_encoding_net(x_t, f, 32, radii, ks, mlps, [], True, 0.9, "ctx", use_xyz=True, shift_pred=shift,
+                                                        fps_idx=fps, variables=st)
+    assert tuple(out.shape) == (2, 32, 96) and sp is shift
+    gout = T(rng.randn(*out.shape).astype(np.float32), cuda)
+    out.backward(gout)
+    assert shift.grad is None
+    new_xyz = oracle.gather_point(xyz, N(fps))
+    wants = []
+    for i, (r, k) in enumerate(zip(radii, ks)):
+        eidx, _ = oracle.query_ball_point(r, k, xyz, new_xyz)
+        ii = T(eidx.astype(np.int64), cuda)
+        gx = torch.stack([x_t[b][ii[b]] for b in range(2)]) - T(new_xyz, cuda).unsqueeze(2) - T(shift_np, cuda).unsqueeze(2)
+        gp = torch.stack([fr[b][ii[b]] for b in range(2)])
+        wants.append(torch_mlp_train(torch.cat([gp, gx], dim=-1).reshape(-1, 6), ref[i], 0.9, k).reshape(2, 32, 32))
+    want = torch.cat(wants, dim=-1)
+    want.backward(gout)
+    np.testing.assert_allclose(N(out), N(want), **TRAIN_TOL)
+    np.testing.assert_allclose(N(f.grad), N(fr.grad), **TRAIN_TOL)
+    for la, lb in zip(mine, ref):
+        for a, b_ in zip(la, lb):
+            for key in ("weights", "biases", "gamma", "beta"):
+                np.testing.assert_allclose(N(a[key].grad), N(b_[key].grad), rtol=2e-3, atol=5e-4, err_msg=key)
+    # the inference form afterwards runs on the updated moving averages and the same variables
+    _, inf, _, _ = context_encoder.multi_encoding_net(x_t, T(col, cuda), 32, radii, ks, mlps, [], False, None, "ctx", use_xyz=True,
+                                                      shift_pred=T(shift_np, cuda), fps_idx=fps, variables=st)
+    assert inf.shape == out.shape
 
 
 def test_fp_module_training_forward_backward(cuda, oracle):
