@@ -17,7 +17,10 @@
 //     touched bucket: one distance per lane, redux.sync max, winner lane (key tie-break only on an exact tie), state to lane j.
 //     the warp's candidate = best of its 32 bucket maxima, recomputed only when one of them moved; then the same st.async /
 //     mbarrier all-to-all and table reduce as fps.cu.
-// Measured on config 2: ~13 bucket updates per round in the whole cluster instead of 1024.
+// Measured on config 2: 12.9 bucket updates per round in the whole cluster instead of 1024 -- and 1.55 ms instead of 1.06 ms: every
+// round some warp holds the sample's bucket and runs update -> bucket argmax -> warp argmax -> send (~650 dependent cycles) while the
+// other 31 wait in the exchange; the full scan's 394 cycles of pipelined FFMA2 are a shorter critical path.  Opt-in
+// (gspn_fps_tune(2)), kept with its tests as the record of that result.
 #include "fps_common.cuh"
 
 namespace cg = cooperative_groups;

@@ -1,5 +1,6 @@
-"""Per-phase cycle breakdown of the FPS round (gspn_fps_profile: full-scan cluster kernels) and the bucket-pruned kernel's
-cycles / bucket updates per round (gspn_fps_bucket_profile), plus CUDA-event timings of both on config 2's SA1. Run under gpurun."""
+"""Per-phase cycle breakdown of the FPS round (gspn_fps_profile: full-scan cluster kernels), the two bucket-pruned kernels' cycles /
+bucket updates per round (gspn_fps_pruned_profile: cluster form, gspn_fps_bucket_profile: single-CTA form), plus CUDA-event timings of
+all three on config 2's SA1. Run under gpurun."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
