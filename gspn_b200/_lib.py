@@ -69,6 +69,7 @@ SIGNATURES = {
     "gspn_mlp_chain_set_profile": (None, [P]),
     "gspn_mlp_chain_tune": (None, [c_int, c_int, c_int]),
     "gspn_mlp_chain_tune_fp": (None, [c_int]),
+    "gspn_mlp_chain_plan": (c_int, [c_int, c_long, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     "gspn_mlp_chain_tune_sched": (None, [c_int]),
     "gspn_col_moments_f32": (c_int, [c_long, c_int, P, P, P, P]),
     "gspn_bn_act_f32": (c_int, [c_long, c_int, P, P, P, P, P, c_int, P, P]),

@@ -1048,14 +1048,20 @@ static cudaError_t launch_variant(const ChainParams &p, const CUtensorMap &tm_f3
 
 // dims[0] = K0 (multiple of 64: the operand blocks the ring carries), dims[l+1] = cout of layer l; k0_used = real columns of layer 0's
 // operand (0: all of K0).
+// plan_out != nullptr: plan only (gspn_mlp_chain_plan) -- no device, no pointers but the two output sentinels, nothing launched;
+// plan_out[0..11] = CTAs per SM, epilogue warps, threads per CTA, weight rows per ring stage, accumulator columns per buffer,
+// accumulator buffers, TMEM columns allocated, TMEM column of the activation operand, operand ring stages, weight ring stages,
+// dynamic shared memory bytes, passes of the last layer.
 static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, int k0_used, const void *const *wimg, const float *const *scale,
                         const float *const *shift, const int *relu, int pool, float *out_f32, void *out_h, int out_h_dtype, int arith,
-                        gspn_stream_t stream) {
+                        gspn_stream_t stream, int *plan_out = nullptr) {
+    const bool plan_only = plan_out != nullptr;
     GSPN_REQUIRE(rows >= 0 && nlayers >= 1 && nlayers <= kMaxLayers && pool >= 1);
-    GSPN_REQUIRE_PTR(dims); GSPN_REQUIRE_PTR(wimg); GSPN_REQUIRE_PTR(scale); GSPN_REQUIRE_PTR(shift); GSPN_REQUIRE_PTR(relu);
+    GSPN_REQUIRE_PTR(dims);
+    if (!plan_only) { GSPN_REQUIRE_PTR(wimg); GSPN_REQUIRE_PTR(scale); GSPN_REQUIRE_PTR(shift); GSPN_REQUIRE_PTR(relu); }
     if (!arith_ok(arith)) return GSPN_E_BAD_DTYPE;
     if (out_h && out_h_dtype != GSPN_DT_BF16 && out_h_dtype != GSPN_DT_F16) return GSPN_E_BAD_DTYPE;
-    if (rows == 0) return GSPN_OK;
+    if (rows == 0) return plan_only ? GSPN_E_BAD_SHAPE : GSPN_OK;
     if (out_f32 == nullptr && out_h == nullptr) return GSPN_E_NULL_PTR;
     const bool split = arith == GSPN_MLP_BF16X3;
     p.rows = rows;
@@ -1071,11 +1077,13 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
         p.N[l] = dims[l + 1];
         GSPN_REQUIRE(p.N[l] > 0);
         if (p.N[l] % 32 != 0 || p.N[l] > 512) return GSPN_E_UNSUPPORTED;  // use the fp32 path
-        GSPN_REQUIRE_PTR(wimg[l]); GSPN_REQUIRE_PTR(scale[l]); GSPN_REQUIRE_PTR(shift[l]);
-        p.wimg[l] = (const unsigned char *)wimg[l];
-        p.scale[l] = scale[l];
-        p.shift[l] = shift[l];
-        p.relu[l] = relu[l];
+        if (!plan_only) {
+            GSPN_REQUIRE_PTR(wimg[l]); GSPN_REQUIRE_PTR(scale[l]); GSPN_REQUIRE_PTR(shift[l]);
+            p.wimg[l] = (const unsigned char *)wimg[l];
+            p.scale[l] = scale[l];
+            p.shift[l] = shift[l];
+        }
+        p.relu[l] = relu ? relu[l] : 1;
         maxn = p.N[l] > maxn ? p.N[l] : maxn;
         if (l + 1 < nlayers) {
             dmid = p.N[l] > dmid ? p.N[l] : dmid;
@@ -1085,7 +1093,7 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     }
     if (nlayers == 1) dmid = p.N[0];  // a single layer never runs in passes (that would re-read the operand ring)
     if (pool > 1) {
-        if (pool % 32 != 0 || rows % pool != 0 || !relu[nlayers - 1]) return GSPN_E_UNSUPPORTED;
+        if (pool % 32 != 0 || rows % pool != 0 || !p.relu[nlayers - 1]) return GSPN_E_UNSUPPORTED;
         if (pool != 32 && (out_f32 == nullptr || out_h != nullptr)) return GSPN_E_UNSUPPORTED;
     }
     p.prof = g_tune.prof;
@@ -1094,19 +1102,22 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     p.out_f32_vec = (reinterpret_cast<uintptr_t>(out_f32) & 31u) == 0;
     p.out_h = out_h;
     p.out_h_f16 = out_h_dtype == GSPN_DT_F16;
-    DevInfo *di = nullptr;
-    { int rc = device_info(&di); if (rc != GSPN_OK) return rc; }
+    static DevInfo b200 = {148};
+    DevInfo *di = &b200;
+    if (!plan_only) { int rc = device_info(&di); if (rc != GSPN_OK) return rc; }
     // pool == 1 outputs leave through TMA tensor stores from per-warp staging boxes
     CUtensorMap tm_f32, tm_h;
     memset(&tm_f32, 0, sizeof(tm_f32));
     memset(&tm_h, 0, sizeof(tm_h));
     p.tma_out = pool == 1 && g_tune.tma_out;
-    if (p.tma_out && out_f32) p.tma_out = encode_out_map(&tm_f32, out_f32, rows, p.N[nlayers - 1], 0);
-    if (p.tma_out && out_h) p.tma_out = encode_out_map(&tm_h, out_h, rows, p.N[nlayers - 1], p.out_h_f16 ? 2 : 1);
+    if (!plan_only) {
+        if (p.tma_out && out_f32) p.tma_out = encode_out_map(&tm_f32, out_f32, rows, p.N[nlayers - 1], 0);
+        if (p.tma_out && out_h) p.tma_out = encode_out_map(&tm_h, out_h, rows, p.N[nlayers - 1], p.out_h_f16 ? 2 : 1);
+    }
     p.stg_h_off = out_f32 ? 4096u : 0u;
     p.stg_bytes = p.tma_out ? (uint32_t)((out_f32 ? 4096 : 0) + (out_h ? 2048 : 0)) : 0u;
     cudaStream_t s = as_stream(stream);
-    if (pool > 1 && pool != 32)
+    if (!plan_only && pool > 1 && pool != 32)
         GSPN_CUDA_OK(cudaMemsetAsync(out_f32, 0, sizeof(float) * (size_t)(rows / pool) * p.N[nlayers - 1], s));
 
     // Plan.  TMEM (512 columns per SM): [accumulator buffer(s) of dcols columns | activation operand hi | lo]; mid layers need their
@@ -1147,6 +1158,8 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     const int nch0 = maxn < 128 ? maxn : 128;
     // the feature-propagation producer needs its eight gather warps' registers: one CTA per SM
     for (int o = (p.mode == kModeFP ? 1 : g_tune.occ_cap); o >= 1; --o) {
+        // (a plan with ONE operand stage -- split arithmetic at two CTAs per SM: SA2, SA3, config 3 -- was A/B-ed against 64-row weight
+        // stages + two operand stages: 0.070 vs 0.070 ms (SA2), 0.060 vs 0.062 ms (SA3): the co-resident CTA already covers the refill)
         if (plan(o, nch0)) break;
         if (nch0 > 64 && plan(o, 64)) break;
     }
@@ -1162,6 +1175,13 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     long grid = (long)di->sms * occ;
     if (grid > p.ntiles || p.dyn_tiles) grid = p.ntiles;
     if (grid > 0x7FFFFFFFL) return GSPN_E_UNSUPPORTED;
+    if (plan_only) {
+        const int npw = p.mode == kModeBulk ? 1 : (p.mode == kModeGatherSA ? 2 : g_tune.fp_warps);
+        const int vals[12] = {occ, p.epi_warps, (p.epi_warps + npw + 2) * 32, p.nch, p.dcols, p.tm_bufs, p.tmem_cols, p.a_col, p.a_stages,
+                              p.w_stages, (int)smem, (p.N[nlayers - 1] + p.dcols - 1) / p.dcols};
+        for (int i = 0; i < 12; ++i) plan_out[i] = vals[i];
+        return GSPN_OK;
+    }
     int dev = 0;
     GSPN_CUDA_OK(cudaGetDevice(&dev));
     cudaError_t e = cudaErrorInvalidValue;
@@ -1185,6 +1205,18 @@ static int chain_launch(ChainParams p, long rows, int nlayers, const int *dims, 
     if (e == cudaSuccess) attr_done[dev][variant] = 1;
     if (e != cudaSuccess) { set_last_cuda_error(e); return GSPN_E_CUDA; }
     return check_launch();
+}
+
+// What the launcher would do for a chain of this shape, without a device: mode 0 = tile image (gspn_mlp_chain), 1 = in-chain gather
+// (gspn_mlp_chain_gather), 2 = feature propagation (gspn_mlp_chain_fp: dims start at the first MMA layer's input, n0).
+extern "C" int gspn_mlp_chain_plan(int mode, long rows, int nlayers, const int *dims, int k0_used, int pool, int want_f32, int want_h, int arith,
+                                   int *plan12) {
+    GSPN_REQUIRE(mode >= 0 && mode <= 2);
+    GSPN_REQUIRE_PTR(plan12);
+    ChainParams p = {};
+    p.mode = mode == 0 ? kModeBulk : (mode == 1 ? kModeGatherSA : kModeFP);
+    return chain_launch(p, rows, nlayers, dims, k0_used, nullptr, nullptr, nullptr, nullptr, pool, want_f32 ? reinterpret_cast<float *>(64) : nullptr,
+                        want_h ? reinterpret_cast<void *>(64) : nullptr, GSPN_DT_F16, arith, nullptr, plan12);
 }
 
 extern "C" int gspn_mlp_chain(long rows, int nlayers, const int *dims, int k0_used, const void *a, const void *const *wimg,

@@ -301,6 +301,12 @@ int gspn_group_rows_grad(int b, int n, int c, int m, int nsample, int ld, const 
  * MMA issuer: [5] issue, [6] drain until tcgen05.commit lands, [7] hand-off waits.  NULL switches it off.
  * gspn_mlp_chain_tune: occ_cap 1|2 = most chain CTAs per SM, bufs_cap 1|2 = most TMEM accumulator buffers,
  * tma_out 0 = row-per-lane 256-bit output stores instead of TMA tensor stores.  Defaults (2, 2, 1) are the measured best. */
+/* The plan the launcher makes for a chain of this shape -- no device needed, nothing launched.  mode 0 = gspn_mlp_chain, 1 =
+ * gspn_mlp_chain_gather, 2 = gspn_mlp_chain_fp (dims start at n0).  plan12 = {CTAs per SM, epilogue warps, threads per CTA, weight rows
+ * per ring stage, accumulator columns per buffer, accumulator buffers, TMEM columns allocated, TMEM column of the activation operand,
+ * operand ring stages, weight ring stages, dynamic shared memory bytes, passes of the last layer}. */
+int gspn_mlp_chain_plan(int mode, long rows, int nlayers, const int *dims, int k0_used, int pool, int want_f32, int want_h, int arith,
+                        int *plan12);
 void gspn_mlp_chain_set_profile(long long *prof);
 void gspn_mlp_chain_tune(int occ_cap, int bufs_cap, int tma_out);
 /* gather warps of gspn_mlp_chain_fp: 8 (default; 448 threads, fastest alone) or 4 (320 threads: leaves registers for an FPS CTA on the SM) */

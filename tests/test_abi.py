@@ -139,3 +139,44 @@ def test_product_never_imports_the_oracle():
     for path in glob.glob(os.path.join(ROOT, "gspn_b200", "csrc", "*")):
         if os.path.isfile(path) and not path.endswith(".so"):
             assert "oracle" not in open(path, errors="ignore").read().lower() or path.endswith(".log"), path
+
+
+def test_chain_planner_fits_the_sm_for_every_model_shape():
+    """gspn_mlp_chain_plan: what the launcher would do, without a device.  For every chain of the model (SA1-4, FP1-4 incl. the commuted
+    fa_layer4 and its pre-multiplication, config 3's three balls) and both arithmetics: tensor memory, shared memory and the register
+    file hold the planned number of co-resident CTAs, and the rings are deep enough to be rings."""
+    L = _lib.lib()
+    c = lambda a: ctypes.cast(a, ctypes.c_void_p)
+
+    def plan(mode, rows, dims, k0, pool, want_h, arith):
+        d, out = (ctypes.c_int * len(dims))(*dims), (ctypes.c_int * 12)()
+        rc = L.gspn_mlp_chain_plan(mode, rows, len(dims) - 1, c(d), k0, pool, 1, want_h, arith, c(out))
+        assert rc == 0, (rc, dims)
+        return dict(zip(("occ", "epi", "threads", "nch", "dcols", "bufs", "tmem", "a_col", "a_stages", "w_stages", "smem", "passes"), out))
+
+    shapes = [("sa1", 1, 524288, [64, 32, 32, 64], 6, 32, 0), ("sa2", 0, 131072, [128, 64, 64, 128], 67, 32, 0),
+              ("sa3", 0, 32768, [192, 128, 128, 256], 131, 32, 0), ("sa4", 0, 8192, [320, 256, 256, 512], 259, 32, 0),
+              ("fp1", 0, 1024, [768, 256, 256], 768, 1, 0), ("fp2", 0, 4096, [384, 256, 256], 384, 1, 0),
+              ("fp3", 0, 16384, [320, 256, 128], 320, 1, 0), ("fp4", 2, 262144, [128, 128, 128], 0, 1, 1),
+              ("fp4_y2", 0, 16384, [128, 128], 128, 1, 0), ("cfg3_r0.5", 1, 16 * 128 * 256, [64, 64, 128, 256], 6, 256, 0),
+              ("cfg3_r1.5", 1, 16 * 128 * 512, [64, 64, 128, 256], 6, 512, 0)]
+    for name, mode, rows, dims, k0, pool, want_h in shapes:
+        for arith in (_lib.GSPN_MLP_BF16, _lib.GSPN_MLP_BF16X3):
+            p = plan(mode, rows, dims, k0, pool, want_h, arith)
+            split = 2 if arith == _lib.GSPN_MLP_BF16X3 else 1
+            mid = max(dims[1:-1]) if len(dims) > 2 else 0
+            assert p["occ"] in (1, 2) and p["occ"] * p["tmem"] <= 512, (name, p)               # tensor memory: 512 columns per SM
+            assert p["tmem"] & (p["tmem"] - 1) == 0 and p["tmem"] >= 32                           # allocations are powers of two
+            assert p["a_col"] == p["bufs"] * p["dcols"] and p["a_col"] + split * mid // 2 <= p["tmem"], (name, p)
+            assert p["dcols"] >= mid and p["dcols"] % p["nch"] == 0                               # a middle layer never runs in passes
+            assert p["passes"] == -(-dims[-1] // p["dcols"])
+            assert p["occ"] * (p["smem"] + 1024) <= 228 * 1024 and p["smem"] <= 226 * 1024, (name, p)
+            assert (p["occ"] + 1) * (p["smem"] + 1024) > 228 * 1024, (name, p)                  # ... and no more CTAs than planned
+            assert p["threads"] == (p["epi"] + {0: 1, 1: 2, 2: 8}[mode] + 2) * 32
+            assert p["occ"] * p["threads"] * (128 if p["threads"] != 352 else 168) <= 65536, (name, p)  # registers (launch bounds)
+            assert p["w_stages"] >= 2 and p["a_stages"] >= (2 if mode == 2 else 1)
+    # nothing the kernel cannot run is planned: widths must be multiples of 32 up to 512, at most four layers
+    d, out = (ctypes.c_int * 3)(64, 48, 520), (ctypes.c_int * 12)()
+    assert L.gspn_mlp_chain_plan(0, 128, 2, c(d), 0, 1, 1, 0, _lib.GSPN_MLP_BF16X3, c(out)) == _lib.GSPN_E_UNSUPPORTED
+    assert L.gspn_mlp_chain_plan(3, 128, 2, c(d), 0, 1, 1, 0, _lib.GSPN_MLP_BF16X3, c(out)) == _lib.GSPN_E_BAD_SHAPE
+    assert L.gspn_mlp_chain_plan(0, 0, 2, c(d), 0, 1, 1, 0, _lib.GSPN_MLP_BF16X3, c(out)) == _lib.GSPN_E_BAD_SHAPE
