@@ -28,6 +28,7 @@ ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--precision", default=None)
 ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--nccl-moments", action="store_true", help="A/B: batch-norm moment all-reduces through NCCL instead of NVLink peer memory")
+ap.add_argument("--eager-launch", action="store_true", help="A/B: launch every kernel of the step from Python instead of replaying one CUDA graph")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -43,7 +44,7 @@ B, N, NSMP, NPTS = 2, 18000, 256, 512
 store, _ = backbone.random_variables(dev)  # same seed on every rank -> identical initial parameters
 offset = torch.zeros(3, device=dev, requires_grad=True)
 params = train.trainable(store) + [offset]
-opt = torch.optim.Adam(params, lr=1e-3)
+opt = torch.optim.Adam(params, lr=1e-3, capturable=not args.eager_launch)  # capturable: the step count lives on the device
 g = torch.Generator(device="cpu").manual_seed(1234 + rank)
 total = args.warmup + args.steps
 batches = []
@@ -54,7 +55,10 @@ for step in range(total):
 
 
 def step_fn(i):
-    x, c, sel = batches[i]
+    return step_on(*batches[i])
+
+
+def step_on(x, c, sel):
     out = backbone.forward(x, c, store, is_training=True, bn_decay=0.9)
     gt = gspn_b200.gather_point(x, sel).reshape(B * NSMP, NPTS, 3)           # 256 proposal sets of 512 points per scene
     pred = gt.flip(1) * 0.98 + offset                                          # stand-in for the generated shapes
@@ -66,6 +70,38 @@ def step_fn(i):
     opt.step()
     return loss
 
+
+graph = None
+if not args.eager_launch:
+    # The whole step -- forward, backward, both kinds of all-reduce, Adam -- is a few thousand small launches: captured ONCE into a CUDA
+    # graph and replayed on static input buffers (the step has no host synchronisation: equal shards, device-side epochs in the peer
+    # all-reduce, capturable Adam).  Every rank captures and replays in lockstep.
+    static = [torch.empty_like(t) for t in batches[0]]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(min(3, args.warmup)):  # eager steps first: optimizer state, cached weight permutations, allocator pools
+            loss = step_fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    try:
+        with torch.cuda.graph(graph):
+            static_loss = step_on(*static)
+    except Exception as e:  # a capture that fails falls back to eager launches, and says so in the JSON line
+        print("bench_cfg4: CUDA-graph capture failed (%s); launching eagerly" % (e,), file=sys.stderr)
+        graph = None
+        torch.cuda.synchronize()
+    if graph is not None:
+        eager_step = step_fn
+
+        def step_fn(i):  # noqa: F811 -- from here on a step is a copy into the static buffers and one graph launch
+            for dst, src in zip(static, batches[i]):
+                dst.copy_(src, non_blocking=True)
+            graph.replay()
+            return static_loss
 
 for i in range(args.warmup):
     loss = step_fn(i)
@@ -94,7 +130,7 @@ if rank == 0:
         "value": world * B / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (training form: CUDA-core GEMMs)", "data": "synthetic",
         "config": {"workload": "config4: data-parallel train step, 2 scenes x 18000 pts per GPU, 256 proposals/scene, NCCL all-reduce of "
-                               "gradients + whole-batch batch-norm statistics", "sync_bn": bool(train.SYNC_BN), "moment_allreduce": "NVLink peer memory (csrc/p2p.cu)" if peer is not None else ("NCCL" if world > 1 else "none"), "params": int(sum(p.numel() for p in params))},
+                               "gradients + whole-batch batch-norm statistics", "sync_bn": bool(train.SYNC_BN), "launch": "eager" if graph is None else "one CUDA graph per step (forward + backward + all-reduces + Adam)", "moment_allreduce": "NVLink peer memory (csrc/p2p.cu)" if peer is not None else ("NCCL" if world > 1 else "none"), "params": int(sum(p.numel() for p in params))},
         "loss": float(loss.detach()), "parameters_identical_across_ranks": same}))
 if peer is not None:
     peer.close()
