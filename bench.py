@@ -326,8 +326,10 @@ def reference_gpu_column(torch, dev, B):
 
 
 # ------------------------------------------------------------------------------------------ main arm
-def main():
-    ap = argparse.ArgumentParser()
+def make_parser():
+    # no abbreviations: flags this parser does not know are forwarded to the workload scripts, and a prefix of one of its own flags
+    # (--no-graph for --no-graphs) must not be swallowed on the way
+    ap = argparse.ArgumentParser(allow_abbrev=False)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
@@ -347,7 +349,11 @@ def main():
     ap.add_argument("--fp-warps", type=int, default=0, help="A/B door: gather warps of the feature-propagation chain (4 or 8)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"],
                     help="cfg2 = BASELINE.json's headline (default); cfg3 / cfg4 = tools/bench_cfg3.py / tools/bench_cfg4.py under the same launch")
-    args, passthrough = ap.parse_known_args()
+    return ap
+
+
+def main():
+    args, passthrough = make_parser().parse_known_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)

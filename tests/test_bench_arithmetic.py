@@ -54,3 +54,15 @@ def test_peaks_loader_prefers_measured_file(tmp_path, monkeypatch):
     peaks = b.load_peaks()
     assert peaks["hbm_gbs"] > 1000 and peaks["bf16_tflops_sustained"] <= peaks["bf16_tflops"] * 1.01
     assert peaks["source"] in ("measured", "fallback")
+
+
+def test_bench_forwards_unknown_flags_unabbreviated():
+    """Flags bench.py does not know go to tools/bench_<workload>.py; a prefix of one of bench.py's own flags must not be eaten on the
+    way (argparse abbreviations: --no-graph would have matched --no-graphs)."""
+    import bench
+    ap = bench.make_parser()
+    args, rest = ap.parse_known_args(["--workload", "cfg4", "--steps", "3", "--nccl-moments", "--eager-launch", "--no-graph"])
+    assert args.workload == "cfg4" and args.steps == 3 and not args.no_graphs
+    assert rest == ["--nccl-moments", "--eager-launch", "--no-graph"]
+    args, rest = ap.parse_known_args(["--no-graphs", "--depth", "4"])
+    assert args.no_graphs and args.depth == 4 and rest == []
